@@ -1,0 +1,179 @@
+// C-ABI entry points other than the plan (plan.cu): library info, loss, stand-alone pre-modules and the
+// operator-level calls the parity tests use. See include/fervit_b200.h for the contracts.
+#include "common.cuh"
+#include "kernels.h"
+#include "fervit_b200.h"
+
+using namespace fervit;
+
+#define FV_API extern "C" __attribute__((visibility("default")))
+
+static inline cudaStream_t S_(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+FV_API int fervit_abi_version(void) { return FERVIT_ABI_VERSION; }
+FV_API const char* fervit_last_error(void) { return get_error(); }
+FV_API unsigned long long fervit_launch_count(void) { return g_launch_count; }
+
+FV_API int fervit_cross_entropy(const float* logits, const long long* labels, const float* weight,
+                                float label_smoothing, int B, int C, const float* den_in, float grad_scale,
+                                float* loss, float* dlogits, float* den_out, void* stream) {
+  FV_CHECK(logits && labels && loss, "cross_entropy: null argument");
+  return cross_entropy(logits, labels, weight, label_smoothing, B, C, den_in, grad_scale, loss, dlogits, den_out,
+                       S_(stream));
+}
+
+static PreParams to_pre(const fervit_premodules* p) {
+  PreParams q;
+  q.use_spe = p->use_spe; q.use_lwn = p->use_lwn; q.use_res = p->use_lwn_res; q.use_leam = p->use_leam;
+  q.group_embed = p->group_embed; q.layer_embed = p->layer_embed; q.groups = p->groups;
+  q.gamma = p->gamma; q.beta = p->beta; q.gate = p->gate; q.leam_w = p->leam_w; q.eps = p->eps;
+  return q;
+}
+
+FV_API int fervit_premodules_forward(const fervit_premodules* p, const float* x, int B, int L, int D, float* y,
+                                     void* stream) {
+  FV_CHECK(p && x && y, "premodules_forward: null argument");
+  return premodules_fwd<float>(x, B, L, D, to_pre(p), y, nullptr, S_(stream));
+}
+
+FV_API long long fervit_premodules_scratch_floats(int B, int L, int D) {
+  return (long long)premodules_chunks(B) * L * (3LL * D + 2);
+}
+
+FV_API int fervit_premodules_backward(const fervit_premodules* p, const float* x, const float* dy, int B, int L,
+                                      int D, float* dx, float* scratch, float* dgamma, float* dbeta,
+                                      float* dlayer_embed, float* dgroup_embed, float* dgate, float* dleam,
+                                      void* stream) {
+  FV_CHECK(p && x && dy && scratch, "premodules_backward: null argument");
+  if (p->use_lwn) FV_CHECK(dgamma && dbeta, "premodules_backward: LWN gradients required");
+  if (p->use_lwn && p->use_lwn_res) FV_CHECK(dgate != nullptr, "premodules_backward: gate gradient required");
+  if (p->use_spe) FV_CHECK(dlayer_embed && dgroup_embed, "premodules_backward: SPE gradients required");
+  if (p->use_leam) FV_CHECK(dleam != nullptr, "premodules_backward: LEAM gradient required");
+  return premodules_bwd<float>(x, dy, B, L, D, to_pre(p), dx, scratch, dgamma, dbeta, dlayer_embed, dgroup_embed,
+                               dgate, dleam, S_(stream));
+}
+
+FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, const float* bias,
+                                 const float* residual, int M, int N, int K, int act, void* out, float* out_f32,
+                                 void* pre, int force_bn, void* stream) {
+  FV_CHECK(x && W, "linear_forward: null argument");
+  Epilogue e = make_epilogue();
+  e.bias = bias; e.residual = residual; e.act = act; e.out = out; e.out_f32 = out_f32; e.out_pre = pre; e.ldo = N;
+  if (act_dtype == FERVIT_F32)
+    return gemm_f32_simt((const float*)x, K, 1, (const float*)W, K, 1, M, N, K, 1, e, S_(stream));
+  FV_CHECK(act_dtype == FERVIT_BF16, "linear_forward: unknown dtype %d", act_dtype);
+  return gemm_bf16_tc((const bf16*)x, K, false, (const bf16*)W, K, false, M, N, K, 1, force_bn, e, S_(stream));
+}
+
+static int op_wgrad_splits(int act_dtype, int M, int N, int K) {
+  // same policy as the plan (plan.cu: wgrad_splits), restated on the public shapes: dW[N,K] reduced over M rows
+  const int sms = num_sms();
+  if (act_dtype == FERVIT_BF16) {
+    const int tiles = ceil_div(N, 128) * ceil_div(K, 128);
+    int s = sms / (tiles > 0 ? tiles : 1);
+    const int max_s = ceil_div(M, 256);
+    if (s > max_s) s = max_s;
+    if (s < 1) s = 1;
+    return gemm_bf16_tc_effective_splits(M, s);
+  }
+  const int tiles = ceil_div(N, 64) * ceil_div(K, 64);
+  int s = (2 * sms) / (tiles > 0 ? tiles : 1);
+  const int max_s = ceil_div(M, 128);
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  return gemm_f32_simt_effective_splits(M, s);
+}
+
+FV_API long long fervit_linear_wgrad_scratch_floats(int M, int N, int K) {
+  const int a = op_wgrad_splits(FERVIT_BF16, M, N, K), b = op_wgrad_splits(FERVIT_F32, M, N, K);
+  return (long long)(a > b ? a : b) * N * K;
+}
+
+FV_API int fervit_linear_wgrad(int act_dtype, const void* dY, const void* X, int M, int N, int K, float alpha,
+                               float* dW, float* scratch, void* stream) {
+  FV_CHECK(dY && X && dW && scratch, "linear_wgrad: null argument");
+  const int splits = op_wgrad_splits(act_dtype, M, N, K);
+  Epilogue e = make_epilogue();
+  e.ldo = K;
+  if (splits > 1) e.out_f32 = scratch;
+  else { e.out_f32 = dW; e.alpha = alpha; }
+  if (act_dtype == FERVIT_F32) {
+    FV_TRY(gemm_f32_simt((const float*)dY, 1, N, (const float*)X, 1, K, N, K, M, splits, e, S_(stream)));
+  } else {
+    FV_CHECK(act_dtype == FERVIT_BF16, "linear_wgrad: unknown dtype %d", act_dtype);
+    FV_TRY(gemm_bf16_tc((const bf16*)dY, N, true, (const bf16*)X, K, true, N, K, M, splits, 0, e, S_(stream)));
+  }
+  if (splits > 1) FV_TRY(splitk_reduce(scratch, splits, (size_t)N * K, nullptr, alpha, dW, S_(stream)));
+  return 0;
+}
+
+FV_API int fervit_layernorm_forward(int act_dtype, const float* x, const float* gamma, const float* beta, float eps,
+                                    int rows, int E, float* y_f32, void* y_act, float* mean, float* rstd,
+                                    void* stream) {
+  FV_CHECK(x && gamma && beta, "layernorm_forward: null argument");
+  if (act_dtype == FERVIT_F32)
+    return layernorm_fwd<float>(x, gamma, beta, eps, rows, E, y_f32, (float*)y_act, mean, rstd, S_(stream));
+  return layernorm_fwd<bf16>(x, gamma, beta, eps, rows, E, y_f32, (bf16*)y_act, mean, rstd, S_(stream));
+}
+
+FV_API long long fervit_layernorm_scratch_floats(int rows, int E) {
+  return ((long long)layernorm_bwd_grid(rows) + 1) * 2 * E;
+}
+
+FV_API int fervit_layernorm_backward(int act_dtype, const void* dy, const float* x, const float* mean,
+                                     const float* rstd, const float* gamma, const float* dres, int rows, int E,
+                                     float* dx_f32, void* dx_act, float* scratch, float* dgamma, float* dbeta,
+                                     void* stream) {
+  FV_CHECK(dy && x && mean && rstd && gamma, "layernorm_backward: null argument");
+  const bool wg = dgamma != nullptr;
+  if (wg) FV_CHECK(dbeta && scratch, "layernorm_backward: dbeta and scratch are required with dgamma");
+  const Dropout nd = make_dropout(0.f, 0, 0);
+  if (act_dtype == FERVIT_F32) {
+    FV_TRY((layernorm_bwd<float, float>((const float*)dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, (float*)dx_act,
+                                        wg ? scratch : nullptr, nd, S_(stream))));
+  } else {
+    FV_TRY((layernorm_bwd<bf16, bf16>((const bf16*)dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, (bf16*)dx_act,
+                                      wg ? scratch : nullptr, nd, S_(stream))));
+  }
+  if (wg) {
+    const int g = layernorm_bwd_grid(rows);
+    float* tmp = scratch + (size_t)g * 2 * E;
+    FV_TRY(colsum_reduce_partials(scratch, g, 2 * E, tmp, S_(stream)));
+    FV_CUDA(cudaMemcpyAsync(dgamma, tmp, E * sizeof(float), cudaMemcpyDeviceToDevice, S_(stream)));
+    FV_CUDA(cudaMemcpyAsync(dbeta, tmp + E, E * sizeof(float), cudaMemcpyDeviceToDevice, S_(stream)));
+  }
+  return 0;
+}
+
+FV_API int fervit_attention_forward(int act_dtype, const void* qkv, int B, int S, int H, int hd, float dropout_p,
+                                    unsigned long long seed, unsigned int site, void* out, float* lse,
+                                    void* stream) {
+  FV_CHECK(qkv && out, "attention_forward: null argument");
+  const Dropout d = make_dropout(dropout_p, seed, site);
+  if (act_dtype == FERVIT_F32)
+    return attention_fwd<float>((const float*)qkv, (float*)out, lse, B, S, H, hd, d, S_(stream));
+  return attention_fwd<bf16>((const bf16*)qkv, (bf16*)out, lse, B, S, H, hd, d, S_(stream));
+}
+
+FV_API int fervit_attention_backward(int act_dtype, const void* qkv, const void* out, const void* dout,
+                                     const float* lse, int B, int S, int H, int hd, float dropout_p,
+                                     unsigned long long seed, unsigned int site, void* dqkv, void* stream) {
+  FV_CHECK(qkv && out && dout && lse && dqkv, "attention_backward: null argument");
+  const Dropout d = make_dropout(dropout_p, seed, site);
+  if (act_dtype == FERVIT_F32)
+    return attention_bwd<float>((const float*)qkv, (const float*)out, (const float*)dout, lse, (float*)dqkv, B, S, H,
+                                hd, d, S_(stream));
+  return attention_bwd<bf16>((const bf16*)qkv, (const bf16*)out, (const bf16*)dout, lse, (bf16*)dqkv, B, S, H, hd, d,
+                             S_(stream));
+}
+
+FV_API int fervit_dropout_mask(float* out, long long n, float p, unsigned long long seed, unsigned int site,
+                               void* stream) {
+  FV_CHECK(out && n >= 0, "dropout_mask: bad argument");
+  return dropout_mask(out, (size_t)n, make_dropout(p, seed, site), S_(stream));
+}
+
+FV_API int fervit_cast_bf16(const float* src, void* dst, long long n, void* stream) {
+  FV_CHECK(src && dst && n >= 0, "cast_bf16: bad argument");
+  return cast_to_act<bf16>(src, (bf16*)dst, (size_t)n, S_(stream));
+}

@@ -1,0 +1,201 @@
+// Shared device/host helpers for the fervit_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace fervit {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// Error handling: every C-ABI entry returns 0 on success; the message of the last failure is kept
+// per host thread and read back with fervit_last_error().
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define FV_CHECK(cond, ...)                \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::fervit::set_error(__VA_ARGS__);    \
+      return 1;                            \
+    }                                      \
+  } while (0)
+
+#define FV_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      ::fervit::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),       \
+                          __FILE__, __LINE__);                                          \
+      return 2;                                                                         \
+    }                                                                                   \
+  } while (0)
+
+#define FV_LAUNCH_CHECK() FV_CUDA(cudaGetLastError())
+
+#define FV_TRY(expr)          \
+  do {                        \
+    int _s = (expr);          \
+    if (_s != 0) return _s;   \
+  } while (0)
+
+// number of kernels launched by this library since load (bench.py reports it as gpu_launches)
+extern unsigned long long g_launch_count;
+#define FV_COUNT_LAUNCH() (++::fervit::g_launch_count)
+
+int num_sms();
+
+// ---------------------------------------------------------------------------------------------
+// Activation ids used by GEMM epilogues and the oracle alike.
+// ---------------------------------------------------------------------------------------------
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+__device__ __forceinline__ float gelu_fwd(float x) {
+  // exact-erf GELU: torch nn.GELU() default, timm Mlp, AdapterModule (hybrid_latent_vit.py:259)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_bwd(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float act_fwd(int act, float x) {
+  if (act == ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == ACT_GELU) return gelu_fwd(x);
+  return x;
+}
+__device__ __forceinline__ float act_bwd(int act, float pre) {
+  if (act == ACT_RELU) return pre > 0.0f ? 1.0f : 0.0f;
+  if (act == ACT_GELU) return gelu_bwd(pre);
+  return 1.0f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based dropout: keep(seed, site, idx) is a pure function, so backward recomputes the
+// mask instead of storing it, and tests can materialise the very same mask for the oracle.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(site + 1) + idx * 0xD1B54A32D192ED03ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+// threshold = round(p * 2^32); keep iff hash >= threshold
+__host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx,
+                                                   uint32_t threshold) {
+  return mix_hash(seed, site, idx) >= threshold;
+}
+static inline uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t <= 0) return 0u;
+  if (t >= 4294967295.0) return 4294967295u;
+  return (uint32_t)t;
+}
+
+struct Dropout {       // passed by value to kernels; p == 0 disables
+  uint64_t seed;
+  uint32_t site;
+  uint32_t threshold;  // 0 = off
+  float scale;         // 1/(1-p)
+};
+static inline Dropout make_dropout(float p, uint64_t seed, uint32_t site) {
+  Dropout d;
+  d.seed = seed;
+  d.site = site;
+  d.threshold = (p > 0.f) ? drop_threshold(p) : 0u;
+  d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM epilogue contract shared by the SIMT fp32 GEMM and the tcgen05 bf16 GEMM.
+//   v = acc (+ bias[col]); v *= act'(aux[row,col]) if act_bwd; v *= alpha; pre = v; v = act(v);
+//   v = dropout(v); v += residual[orow,col]; v += pos[1 + row % remap_L, col]
+//   orow = row (or (row / L) * (L+1) + 1 + row % L when remap_L > 0: token rows skip the cls slot)
+// ---------------------------------------------------------------------------------------------
+struct Epilogue {
+  const float* bias;       // [N] or null
+  const float* residual;   // fp32 [Mout, ldo] or null
+  const void* aux;         // activation-dtype [M, N] pre-activation for act_bwd, or null
+  const float* alpha_ptr;  // device scalar or null
+  float alpha;             // host scalar (1.0 = none)
+  int act;                 // Act applied forward
+  int act_bwd;             // Act whose derivative at aux multiplies the accumulator
+  void* out;               // activation-dtype output [Mout, ldo] or null
+  float* out_f32;          // fp32 output [Mout, ldo] or null
+  void* out_pre;           // activation-dtype pre-activation output [M, N] or null
+  int remap_L;             // 0 = rows map 1:1
+  const float* pos;        // [(L+1), N] position rows, used with remap_L
+  int ldo;                 // leading dimension of out / out_f32 / residual (elements)
+  Dropout drop;
+};
+
+static inline Epilogue make_epilogue() {
+  Epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.alpha = 1.0f;
+  return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dtype helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  float2 r;
+  r.x = __uint_as_float(v << 16);
+  r.y = __uint_as_float(v & 0xffff0000u);
+  return r;
+}
+
+// Load / store 4 consecutive activation values (16-byte aligned for float, 8-byte for bf16).
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load4<bf16>(const bf16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<bf16>(bf16* p, float4 v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+}  // namespace fervit

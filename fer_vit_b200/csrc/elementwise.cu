@@ -1,0 +1,378 @@
+// Small HBM-bound helpers around the GEMMs: casts / weight caches, im2col, cls rows, token gathers,
+// deterministic column sums, split-K reduction, adapter backward glue.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fervit {
+
+namespace ew {
+
+// ---- fp32 -> activation dtype cast (w+ latents into the A operand of the token projection) ----
+template <typename AT>
+__global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst, size_t n4) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+    store4<AT>(dst + i * 4, v);
+  }
+}
+
+// ---- fp32 [R,C] -> bf16 [R,C] and/or bf16 [C,R] (weight caches: W for forward, W^T for dgrad) ----
+__global__ void weight_cache_kernel(const float* __restrict__ src, int R, int C, bf16* __restrict__ dst,
+                                    bf16* __restrict__ dst_t) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = src[(size_t)r * C + c];
+      if (dst) dst[(size_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) dst_t[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// ---- im2col for stride == kernel patchify (image_vit.py:27-43): x [B,C,H,W] -> A [B*L, C*P*P] ----
+template <typename AT>
+__global__ void im2col_kernel(const float* __restrict__ x, AT* __restrict__ out, int B, int C, int H, int W,
+                              int P) {
+  const int gw = W / P, gh = H / P;
+  const int Kd = C * P * P;
+  const size_t total4 = (size_t)B * gh * gw * Kd / 4;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int k = (int)(e % Kd);
+    const size_t tok = e / Kd;
+    const int px = (int)(tok % gw);
+    const int py = (int)((tok / gw) % gh);
+    const int b = (int)(tok / ((size_t)gw * gh));
+    const int j = k % P, ii = (k / P) % P, c = k / (P * P);
+    const float4 v = *reinterpret_cast<const float4*>(x + (((size_t)b * C + c) * H + (py * P + ii)) * W + px * P + j);
+    store4<AT>(out + e, v);
+  }
+}
+
+// ---- x0[b,0,:] = cls + pos[0] (latent_vit.py:41-44, hybrid_latent_vit.py:218-222, image_vit.py:151-155) ----
+template <typename AT>
+__global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ x0,
+                                AT* __restrict__ x0_at, int B, int S, int E, Dropout drop) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float v = cls[c] + pos[c];
+    if (drop.threshold) {
+      const uint64_t idx = (uint64_t)b * S * E + c;
+      v = drop_keep(drop.seed, drop.site, idx, drop.threshold) ? v * drop.scale : 0.f;
+    }
+    x0[(size_t)b * S * E + c] = v;
+    if (x0_at) x0_at[(size_t)b * S * E + c] = from_f32<AT>(v);
+  }
+}
+
+// ---- input dropout over the token rows of x0 (ImageViT, image_vit.py:156); cls rows handled above ----
+template <typename AT>
+__global__ void token_dropout_kernel(float* __restrict__ x0, AT* __restrict__ x0_at, int B, int S, int E, Dropout drop) {
+  const size_t total = (size_t)B * S * E;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int s = (int)((i / E) % S);
+    if (s == 0) continue;
+    const float v = drop_keep(drop.seed, drop.site, i, drop.threshold) ? x0[i] * drop.scale : 0.f;
+    x0[i] = v;
+    if (x0_at) x0_at[i] = from_f32<AT>(v);
+  }
+}
+
+// ---- dx0 [B,S,E] fp32 rows 1.. -> compact [B*L, E] activation dtype (A operand of the input wgrad) ----
+template <typename AT>
+__global__ void gather_tokens_kernel(const float* __restrict__ dx0, AT* __restrict__ out, int B, int L, int E,
+                                     Dropout drop) {
+  const size_t total4 = (size_t)B * L * E / 4;
+  const int S = L + 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i * 4;
+    const int c = (int)(e % E);
+    const size_t tok = e / E;
+    const int l = (int)(tok % L);
+    const size_t b = tok / L;
+    const size_t src = (b * S + 1 + l) * E + c;
+    float4 v = *reinterpret_cast<const float4*>(dx0 + src);
+    if (drop.threshold) {
+      v.x = drop_keep(drop.seed, drop.site, src + 0, drop.threshold) ? v.x * drop.scale : 0.f;
+      v.y = drop_keep(drop.seed, drop.site, src + 1, drop.threshold) ? v.y * drop.scale : 0.f;
+      v.z = drop_keep(drop.seed, drop.site, src + 2, drop.threshold) ? v.z * drop.scale : 0.f;
+      v.w = drop_keep(drop.seed, drop.site, src + 3, drop.threshold) ? v.w * drop.scale : 0.f;
+    }
+    store4<AT>(out + e, v);
+  }
+}
+
+// ---- deterministic column sum: in [R, C] (row stride ld) -> partial [chunks][C] -> out [C] ----
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int rows_per_chunk,
+                                      float* __restrict__ partial, Dropout drop) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int r0 = blockIdx.y * rows_per_chunk;
+  const int r1 = min(R, r0 + rows_per_chunk);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    float v = to_f32<T>(in[(size_t)r * ld + c]);
+    if (drop.threshold)
+      v = drop_keep(drop.seed, drop.site, (uint64_t)r * ld + c, drop.threshold) ? v * drop.scale : 0.f;
+    s += v;
+  }
+  partial[(size_t)blockIdx.y * C + c] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const float* alpha_ptr,
+                                    float alpha, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * C + c];
+  if (alpha_ptr) alpha *= __ldg(alpha_ptr);
+  out[c] = s * alpha;
+}
+
+// ---- split-K reduction: out[i] = alpha * sum_s partial[s][i] ----
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4, const float* alpha_ptr,
+                                     float alpha, float* __restrict__ out) {
+  if (alpha_ptr) alpha *= __ldg(alpha_ptr);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)s * n4 + i) * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    acc.x *= alpha; acc.y *= alpha; acc.z *= alpha; acc.w *= alpha;
+    *reinterpret_cast<float4*>(out + i * 4) = acc;
+  }
+}
+
+// ---- adapter backward glue (AdapterModule, hybrid_latent_vit.py:249-265):
+//      p = dy W2 (fp32 [T,A]); du = alpha * p * gelu'(u); rowpart[blk] = sum p*g over the CTA's elements ----
+template <typename AT>
+__global__ void __launch_bounds__(256)
+adapter_bwd_kernel(const float* __restrict__ p, const AT* __restrict__ u, const AT* __restrict__ g,
+                   const float* __restrict__ alpha_ptr, size_t n4, AT* __restrict__ du, float* __restrict__ part) {
+  __shared__ float red[8];
+  const float alpha = __ldg(alpha_ptr);
+  float s = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 pv = *reinterpret_cast<const float4*>(p + i * 4);
+    const float4 uv = load4<AT>(u + i * 4);
+    const float4 gv = load4<AT>(g + i * 4);
+    s += (pv.x * gv.x + pv.y * gv.y) + (pv.z * gv.z + pv.w * gv.w);
+    float4 o;
+    o.x = alpha * pv.x * gelu_bwd(uv.x);
+    o.y = alpha * pv.y * gelu_bwd(uv.y);
+    o.z = alpha * pv.z * gelu_bwd(uv.z);
+    o.w = alpha * pv.w * gelu_bwd(uv.w);
+    store4<AT>(du + i * 4, o);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    part[blockIdx.x] = t;
+  }
+}
+// dalpha = sum(part) + b2 . colsum(dy);  db2 = alpha * colsum(dy)
+__global__ void adapter_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ b2,
+                                        const float* __restrict__ dy_colsum, int E, const float* __restrict__ alpha_ptr,
+                                        float* __restrict__ dalpha, float* __restrict__ db2) {
+  __shared__ float red[32];
+  const float alpha = __ldg(alpha_ptr);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    const float cs = dy_colsum[c];
+    s += b2[c] * cs;
+    db2[c] = alpha * cs;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    dalpha[0] = t;
+  }
+}
+
+__global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, Dropout drop) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = drop_keep(drop.seed, drop.site, i, drop.threshold) ? drop.scale : 0.f;
+}
+
+__global__ void fill_kernel(float* __restrict__ out, size_t n, float v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = v;
+}
+
+static inline int grid_for(size_t n, int block) {
+  size_t g = (n + block - 1) / block;
+  const size_t cap = (size_t)num_sms() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace ew
+
+template <typename AT>
+int cast_to_act(const float* src, AT* dst, size_t n, cudaStream_t stream) {
+  FV_CHECK(n % 4 == 0, "cast_to_act: element count must be a multiple of 4");
+  if (n == 0) return 0;
+  ew::cast_kernel<AT><<<ew::grid_for(n / 4, 256), 256, 0, stream>>>(src, dst, n / 4);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int cast_to_act<float>(const float*, float*, size_t, cudaStream_t);
+template int cast_to_act<bf16>(const float*, bf16*, size_t, cudaStream_t);
+
+int weight_cache(const float* src, int R, int C, bf16* dst, bf16* dst_t, cudaStream_t stream) {
+  dim3 grid(ceil_div(C, 32), ceil_div(R, 32)), block(32, 8);
+  ew::weight_cache_kernel<<<grid, block, 0, stream>>>(src, R, C, dst, dst_t);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename AT>
+int im2col(const float* x, AT* out, int B, int C, int H, int W, int P, cudaStream_t stream) {
+  FV_CHECK(P % 4 == 0 && H % P == 0 && W % P == 0, "im2col: patch size must divide the image and be a multiple of 4");
+  const size_t n4 = (size_t)B * C * H * W / 4;
+  ew::im2col_kernel<AT><<<ew::grid_for(n4, 256), 256, 0, stream>>>(x, out, B, C, H, W, P);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int im2col<float>(const float*, float*, int, int, int, int, int, cudaStream_t);
+template int im2col<bf16>(const float*, bf16*, int, int, int, int, int, cudaStream_t);
+
+template <typename AT>
+int cls_rows(const float* cls, const float* pos, float* x0, AT* x0_at, int B, int S, int E, Dropout drop,
+             cudaStream_t stream) {
+  ew::cls_rows_kernel<AT><<<B, 256, 0, stream>>>(cls, pos, x0, x0_at, B, S, E, drop);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int cls_rows<float>(const float*, const float*, float*, float*, int, int, int, Dropout, cudaStream_t);
+template int cls_rows<bf16>(const float*, const float*, float*, bf16*, int, int, int, Dropout, cudaStream_t);
+
+template <typename AT>
+int token_dropout(float* x0, AT* x0_at, int B, int S, int E, Dropout drop, cudaStream_t stream) {
+  if (!drop.threshold) return 0;
+  const size_t n = (size_t)B * S * E;
+  ew::token_dropout_kernel<AT><<<ew::grid_for(n, 256), 256, 0, stream>>>(x0, x0_at, B, S, E, drop);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int token_dropout<float>(float*, float*, int, int, int, Dropout, cudaStream_t);
+template int token_dropout<bf16>(float*, bf16*, int, int, int, Dropout, cudaStream_t);
+
+template <typename AT>
+int gather_tokens(const float* dx0, AT* out, int B, int L, int E, Dropout drop, cudaStream_t stream) {
+  FV_CHECK(E % 4 == 0, "gather_tokens: E must be a multiple of 4");
+  const size_t n4 = (size_t)B * L * E / 4;
+  ew::gather_tokens_kernel<AT><<<ew::grid_for(n4, 256), 256, 0, stream>>>(dx0, out, B, L, E, drop);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int gather_tokens<float>(const float*, float*, int, int, int, Dropout, cudaStream_t);
+template int gather_tokens<bf16>(const float*, bf16*, int, int, int, Dropout, cudaStream_t);
+
+int colsum_chunks(int R) {
+  int chunks = ceil_div(R, 64);
+  if (chunks > 256) chunks = 256;
+  if (chunks < 1) chunks = 1;
+  return chunks;
+}
+
+// scratch: [colsum_chunks(R)][C] fp32
+template <typename T>
+int colsum(const T* in, int R, int C, long long ld, float* scratch, const float* alpha_ptr, float alpha, float* out,
+           Dropout drop, cudaStream_t stream) {
+  const int chunks = colsum_chunks(R);
+  const int rpc = ceil_div(R, chunks);
+  dim3 grid(ceil_div(C, 128), chunks);
+  ew::colsum_partial_kernel<T><<<grid, 128, 0, stream>>>(in, R, C, ld, rpc, scratch, drop);
+  FV_COUNT_LAUNCH();
+  ew::colsum_final_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(scratch, chunks, C, alpha_ptr, alpha, out);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int colsum<float>(const float*, int, int, long long, float*, const float*, float, float*, Dropout,
+                           cudaStream_t);
+template int colsum<bf16>(const bf16*, int, int, long long, float*, const float*, float, float*, Dropout,
+                          cudaStream_t);
+
+int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream) {
+  ew::colsum_final_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(partial, chunks, C, nullptr, 1.0f, out);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
+                  cudaStream_t stream) {
+  FV_CHECK(n % 4 == 0, "splitk_reduce: element count must be a multiple of 4");
+  ew::splitk_reduce_kernel<<<ew::grid_for(n / 4, 256), 256, 0, stream>>>(partial, splits, n / 4, alpha_ptr, alpha, out);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int adapter_bwd_parts(size_t n) { return ew::grid_for(n / 4, 256); }
+
+template <typename AT>
+int adapter_bwd_glue(const float* p, const AT* u, const AT* g, const float* alpha_ptr, size_t n, AT* du, float* part,
+                     cudaStream_t stream) {
+  FV_CHECK(n % 4 == 0, "adapter_bwd_glue: element count must be a multiple of 4");
+  ew::adapter_bwd_kernel<AT><<<adapter_bwd_parts(n), 256, 0, stream>>>(p, u, g, alpha_ptr, n / 4, du, part);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int adapter_bwd_glue<float>(const float*, const float*, const float*, const float*, size_t, float*, float*,
+                                     cudaStream_t);
+template int adapter_bwd_glue<bf16>(const float*, const bf16*, const bf16*, const float*, size_t, bf16*, float*,
+                                    cudaStream_t);
+
+int adapter_finalize(const float* part, int nparts, const float* b2, const float* dy_colsum, int E,
+                     const float* alpha_ptr, float* dalpha, float* db2, cudaStream_t stream) {
+  ew::adapter_finalize_kernel<<<1, 256, 0, stream>>>(part, nparts, b2, dy_colsum, E, alpha_ptr, dalpha, db2);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int dropout_mask(float* out, size_t n, Dropout drop, cudaStream_t stream) {
+  ew::dropout_mask_kernel<<<ew::grid_for(n, 256), 256, 0, stream>>>(out, n, drop);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int fill_f32(float* out, size_t n, float v, cudaStream_t stream) {
+  if (n == 0) return 0;
+  ew::fill_kernel<<<ew::grid_for(n, 256), 256, 0, stream>>>(out, n, v);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace fervit

@@ -1,0 +1,96 @@
+// Internal launch wrappers implemented across the .cu files of this directory.
+#pragma once
+#include "common.cuh"
+
+namespace fervit {
+
+// gemm_tc.cu
+int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool b_mn, int M, int N, int K, int splits,
+                 int force_bn, const Epilogue& epi, cudaStream_t stream);
+int gemm_bf16_tc_effective_splits(int K, int splits);
+// gemm_simt.cu
+int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, int M,
+                  int N, int K, int splits, const Epilogue& epi, cudaStream_t stream);
+int gemm_f32_simt_effective_splits(int K, int splits);
+
+// layernorm.cu
+template <typename AT>
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int E, float* out_f32,
+                  AT* out_at, float* mean, float* rstd, cudaStream_t stream);
+int layernorm_bwd_grid(int rows);
+template <typename DT, typename AT>
+int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* dres, int rows, int E, float* dx_f32, AT* dx_at, float* partial, Dropout at_drop,
+                  cudaStream_t stream);
+
+// elementwise.cu
+template <typename AT> int cast_to_act(const float* src, AT* dst, size_t n, cudaStream_t stream);
+int weight_cache(const float* src, int R, int C, bf16* dst, bf16* dst_t, cudaStream_t stream);
+template <typename AT> int im2col(const float* x, AT* out, int B, int C, int H, int W, int P, cudaStream_t stream);
+template <typename AT>
+int cls_rows(const float* cls, const float* pos, float* x0, AT* x0_at, int B, int S, int E, Dropout drop,
+             cudaStream_t stream);
+template <typename AT>
+int token_dropout(float* x0, AT* x0_at, int B, int S, int E, Dropout drop, cudaStream_t stream);
+template <typename AT>
+int gather_tokens(const float* dx0, AT* out, int B, int L, int E, Dropout drop, cudaStream_t stream);
+int colsum_chunks(int R);
+template <typename T>
+int colsum(const T* in, int R, int C, long long ld, float* scratch, const float* alpha_ptr, float alpha, float* out,
+           Dropout drop, cudaStream_t stream);
+int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream);
+int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
+                  cudaStream_t stream);
+int adapter_bwd_parts(size_t n);
+template <typename AT>
+int adapter_bwd_glue(const float* p, const AT* u, const AT* g, const float* alpha_ptr, size_t n, AT* du, float* part,
+                     cudaStream_t stream);
+int adapter_finalize(const float* part, int nparts, const float* b2, const float* dy_colsum, int E,
+                     const float* alpha_ptr, float* dalpha, float* db2, cudaStream_t stream);
+int dropout_mask(float* out, size_t n, Dropout drop, cudaStream_t stream);
+int fill_f32(float* out, size_t n, float v, cudaStream_t stream);
+
+// attention.cu
+template <typename AT>
+int attention_fwd(const AT* qkv, AT* out, float* lse, int B, int S, int H, int HD, Dropout drop, cudaStream_t stream);
+template <typename AT>
+int attention_bwd(const AT* qkv, const AT* out, const AT* dout, const float* lse, AT* dqkv, int B, int S, int H,
+                  int HD, Dropout drop, cudaStream_t stream);
+
+// head_ce.cu
+int head_fwd(const float* x, int B, int S, int E, const float* gamma, const float* beta, float eps, const float* W,
+             const float* bias, int C, Dropout drop, float* logits, float* mean, float* rstd, cudaStream_t stream);
+int head_wgrad_chunks(int B);
+template <typename AT>
+int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const float* gamma, const float* beta,
+             const float* W, int C, const float* mean, const float* rstd, Dropout drop, float* dx_f32, AT* dx_at,
+             int wgrad, float* scratch, float* dW, float* dgamma, float* dbeta, float* dbias, cudaStream_t stream);
+int cross_entropy(const float* logits, const long long* labels, const float* weight, float smoothing, int B, int C,
+                  const float* den_in, float grad_scale, float* loss, float* dlogits, float* den_out,
+                  cudaStream_t stream);
+
+// premodules.cu
+namespace pre {
+struct Params {
+  int use_spe, use_lwn, use_res, use_leam;
+  const float* group_embed;  // [3, D]
+  const float* layer_embed;  // [L, D]
+  const long long* groups;   // [L]
+  const float* gamma;        // [L, D]
+  const float* beta;         // [L, D]
+  const float* gate;         // [L]
+  const float* leam_w;       // [L]
+  float eps;
+};
+}  // namespace pre
+typedef pre::Params PreParams;
+template <typename AT>
+int premodules_fwd(const float* x, int B, int L, int D, const PreParams& p, float* out_f32, AT* out_at,
+                   cudaStream_t stream);
+int premodules_chunks(int B);
+template <typename DT>
+int premodules_bwd(const float* x, const DT* dy, int B, int L, int D, const PreParams& p, float* dx, float* scratch,
+                   float* dgamma, float* dbeta, float* dlayer, float* dgroup, float* dgate, float* dleam,
+                   cudaStream_t stream);
+
+}  // namespace fervit

@@ -1,0 +1,213 @@
+// LayerNorm forward / backward over the fp32 residual stream, one warp per token row, fp32 statistics.
+// Replaces ATen native_layer_norm behind timm Block.norm1/norm2 (eps 1e-6, hybrid_latent_vit.py:227-233),
+// nn.TransformerEncoderLayer.norm1/norm2 (eps 1e-5, latent_vit.py:24-31, image_vit.py:101-113).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fervit {
+
+namespace ln {
+
+constexpr int MAXCH = 8;  // 8 chunks x 32 lanes x 4 floats = E up to 1024
+constexpr int WARPS = 8;
+
+template <typename AT>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              float eps, int rows, int E, float* __restrict__ out_f32, AT* __restrict__ out_at,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * E;
+  float4 v[MAXCH];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < E) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)E;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < E) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)E + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < MAXCH; ++i) {
+    const int c = lane * 4 + i * 128;
+    if (c < E) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out_f32) *reinterpret_cast<float4*>(out_f32 + (size_t)row * E + c) = y;
+      if (out_at) store4<AT>(out_at + (size_t)row * E + c, y);
+    }
+  }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres). Optional per-CTA partial sums of
+// dgamma = sum dy*xhat and dbeta = sum dy, reduced afterwards in a fixed order (deterministic).
+template <typename DT, typename AT, bool WGRAD>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+              int rows, int E, float* __restrict__ dx_f32, AT* __restrict__ dx_at, float* __restrict__ partial,
+              Dropout at_drop) {
+  __shared__ float red[WGRAD ? WARPS * 32 * 4 : 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 dg[WGRAD ? MAXCH : 1], db[WGRAD ? MAXCH : 1];
+  if (WGRAD) {
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 xh[MAXCH], gd[MAXCH];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < E) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)row * E + c);
+        const float4 d = load4<DT>(dy + (size_t)row * E + c);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        gd[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+        s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+        s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+        if (WGRAD) {
+          dg[i].x += d.x * xh[i].x; dg[i].y += d.y * xh[i].y; dg[i].z += d.z * xh[i].z; dg[i].w += d.w * xh[i].w;
+          db[i].x += d.x; db[i].y += d.y; db[i].z += d.z; db[i].w += d.w;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)E;
+    s2 = warp_sum(s2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c = lane * 4 + i * 128;
+      if (c < E) {
+        float4 o;
+        o.x = rs * (gd[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (gd[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (gd[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (gd[i].w - s1 - xh[i].w * s2);
+        if (dres) {
+          const float4 r = *reinterpret_cast<const float4*>(dres + (size_t)row * E + c);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + (size_t)row * E + c) = o;
+        if (dx_at) {
+          if (at_drop.threshold) {
+            // the activation-dtype copy feeds the dgrad/wgrad of a sub-layer whose output went through dropout
+            const uint64_t base = (uint64_t)row * E + c;
+            o.x = drop_keep(at_drop.seed, at_drop.site, base + 0, at_drop.threshold) ? o.x * at_drop.scale : 0.f;
+            o.y = drop_keep(at_drop.seed, at_drop.site, base + 1, at_drop.threshold) ? o.y * at_drop.scale : 0.f;
+            o.z = drop_keep(at_drop.seed, at_drop.site, base + 2, at_drop.threshold) ? o.z * at_drop.scale : 0.f;
+            o.w = drop_keep(at_drop.seed, at_drop.site, base + 3, at_drop.threshold) ? o.w * at_drop.scale : 0.f;
+          }
+          store4<AT>(dx_at + (size_t)row * E + c, o);
+        }
+      }
+    }
+  }
+  if (WGRAD) {
+    // cross-warp reduction in shared memory, chunk by chunk; partial layout [grid][2][E]
+    float* pg = partial + (size_t)blockIdx.x * 2 * E;
+    float* pb = pg + E;
+#pragma unroll
+    for (int i = 0; i < MAXCH; ++i) {
+      const int c0 = i * 128;
+      if (c0 >= E) break;  // block-uniform
+      for (int which = 0; which < 2; ++which) {
+        const float4 val = which == 0 ? dg[i] : db[i];
+        *reinterpret_cast<float4*>(&red[(warp * 32 + lane) * 4]) = val;
+        __syncthreads();
+        if (warp == 0) {
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int w = 0; w < WARPS; ++w) {
+            const float4 t = *reinterpret_cast<const float4*>(&red[(w * 32 + lane) * 4]);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+          }
+          const int c = c0 + lane * 4;
+          if (c < E) *reinterpret_cast<float4*>((which == 0 ? pg : pb) + c) = acc;
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+}  // namespace ln
+
+template <typename AT>
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int E, float* out_f32,
+                  AT* out_at, float* mean, float* rstd, cudaStream_t stream) {
+  FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  if (rows <= 0) return 0;
+  ln::ln_fwd_kernel<AT><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(x, gamma, beta, eps, rows, E,
+                                                                               out_f32, out_at, mean, rstd);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int layernorm_bwd_grid(int rows) {
+  int g = ceil_div(rows, ln::WARPS);
+  const int cap = num_sms() * 2;
+  return g < cap ? g : cap;
+}
+
+// partial: [layernorm_bwd_grid(rows)][2][E] fp32 when wgrad is requested (else null)
+template <typename DT, typename AT>
+int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                  const float* dres, int rows, int E, float* dx_f32, AT* dx_at, float* partial, Dropout at_drop,
+                  cudaStream_t stream) {
+  FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  if (rows <= 0) return 0;
+  if (partial) {
+    const int grid = layernorm_bwd_grid(rows);
+    ln::ln_bwd_kernel<DT, AT, true><<<grid, ln::WARPS * 32, 0, stream>>>(dy, x, mean, rstd, gamma, dres, rows, E,
+                                                                        dx_f32, dx_at, partial, at_drop);
+  } else {
+    ln::ln_bwd_kernel<DT, AT, false><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(
+        dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at, nullptr, at_drop);
+  }
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+template int layernorm_fwd<float>(const float*, const float*, const float*, float, int, int, float*, float*, float*,
+                                  float*, cudaStream_t);
+template int layernorm_fwd<bf16>(const float*, const float*, const float*, float, int, int, float*, bf16*, float*,
+                                 float*, cudaStream_t);
+template int layernorm_bwd<float, float>(const float*, const float*, const float*, const float*, const float*,
+                                         const float*, int, int, float*, float*, float*, Dropout, cudaStream_t);
+template int layernorm_bwd<bf16, bf16>(const bf16*, const float*, const float*, const float*, const float*,
+                                       const float*, int, int, float*, bf16*, float*, Dropout, cudaStream_t);
+template int layernorm_bwd<float, bf16>(const float*, const float*, const float*, const float*, const float*,
+                                        const float*, int, int, float*, bf16*, float*, Dropout, cudaStream_t);
+
+}  // namespace fervit

@@ -1,0 +1,229 @@
+/* fervit_b200 — C ABI of the B200-native (sm_100a) LatentViT / HybridLatentViT / ImageViT train-step path.
+ *
+ * The reference (yuki-ominato/FER-ViT) has no FFI of its own: its boundary for this path is the Python
+ * nn.Module surface. This header is what a binding for that surface talks to; the Python
+ * host layer in fer_vit_b200/ (ctypes) is such a binding. Every entry point
+ *   - takes raw device pointers, explicit sizes and a cudaStream_t (as void*), never a torch type;
+ *   - returns 0 on success, non-zero on failure (message via fervit_last_error()), never throws;
+ *   - launches asynchronously on the given stream and is CUDA-graph capturable (no host sync, no allocation).
+ * There is no CPU fallback: without a CUDA device the compute entry points fail.
+ *
+ * Each declaration cites the reference interface it replaces (file:line under the reference repo).
+ */
+#ifndef FERVIT_B200_H_
+#define FERVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FERVIT_ABI_VERSION 1
+
+/* ----------------------------------------------------------------------------------------------
+ * Library
+ * -------------------------------------------------------------------------------------------- */
+int fervit_abi_version(void);
+const char* fervit_last_error(void);
+/* number of kernels this library has launched since load (bench.py: gpu_launches) */
+unsigned long long fervit_launch_count(void);
+
+/* dtypes of activation buffers */
+#define FERVIT_F32 0  /* fp32 mode: CUDA-core fp32 GEMMs, the 1e-4 parity mode                      */
+#define FERVIT_BF16 1 /* bf16 mode: tcgen05/TMEM GEMMs fed by TMA, fp32 accumulate, fp32 residual   */
+
+#define FERVIT_ACT_NONE 0
+#define FERVIT_ACT_RELU 1 /* nn.TransformerEncoderLayer default (latent_vit.py:24-30)                */
+#define FERVIT_ACT_GELU 2 /* exact-erf GELU: timm Mlp, AdapterModule, image_vit.py:106              */
+
+/* ----------------------------------------------------------------------------------------------
+ * Whole-model plan: the forward / backward of one model instance.
+ * Replaces, for the three model classes,
+ *   LatentViT.forward            models_fer_vit/latent_vit.py:38-48
+ *   LatentViTv2.forward          models_fer_vit/latent_vit_v2.py:75-85   (SPE -> LWN -> LEAM pre-modules)
+ *   HybridLatentViT.forward      models_fer_vit/hybrid_latent_vit.py:205-239 (+ AdapterModule :249-265,
+ *                                timm Block semantics SURVEY.md §8a row a9)
+ *   ImageViT.forward             models_fer_vit/image_vit.py:138-166 (+ PatchEmbedding :34-44)
+ * and the autograd backward of each (loss.backward(), train_hybrid_latent_vit.py:134).
+ * -------------------------------------------------------------------------------------------- */
+typedef struct fervit_plan fervit_plan;
+
+typedef struct fervit_config {
+  int mode;          /* FERVIT_F32 | FERVIT_BF16 */
+  int input_kind;    /* 0: latent tokens x[B,L,Din] (Linear); 1: image x[B,img_c,img_h,img_w] (Conv2d k=s=patch) */
+  int L;             /* tokens per sample without the cls token (18 w+ layers, 196 patches) */
+  int Din;           /* latent_dim, or img_c*patch*patch */
+  int E;             /* embed dim */
+  int depth;         /* transformer blocks */
+  int H;             /* heads; head dim E/H must be 32, 48 or 64 */
+  int F;             /* MLP hidden dim */
+  int C;             /* classes (<= 16) */
+  int norm_first;    /* 1: pre-norm timm Block; 0: post-norm nn.TransformerEncoderLayer */
+  int act;           /* FERVIT_ACT_RELU | FERVIT_ACT_GELU */
+  float eps_block;   /* 1e-6 timm, 1e-5 torch */
+  float eps_head;    /* 1e-5 */
+  int adapter_dim;   /* 0: none; else bottleneck width of AdapterModule after every block */
+  float dropout;     /* p of the torch layers' four dropout sites (and ImageViT input dropout); 0 for timm */
+  float head_dropout;/* Hybrid head nn.Dropout(0.1), hybrid_latent_vit.py:112 */
+  int input_dropout; /* 1: apply `dropout` to cls+tokens+pos (image_vit.py:156) */
+  int img_c, img_h, img_w, patch;
+  int use_spe, use_lwn, use_lwn_res, use_leam; /* LatentViTv2 pre-modules */
+  float eps_lwn;     /* 1e-5 */
+} fervit_config;
+
+/* Parameter slots. params[] / grads[] arrays are indexed FERVIT_G_* for globals and
+ * FERVIT_NUM_GLOBAL + block * FERVIT_NUM_BLOCK + FERVIT_B_* for block parameters.
+ * All parameters are fp32, contiguous, in the reference's own layouts (nn.Linear weight = [out, in]). */
+enum {
+  FERVIT_G_IN_W = 0,     /* input_proj.weight [E,Din] | patch_embed.proj.weight [E, img_c*patch*patch] */
+  FERVIT_G_IN_B,         /* [E] */
+  FERVIT_G_CLS,          /* cls_token [E] */
+  FERVIT_G_POS,          /* pos_emb / pos_embed [(L+1),E] */
+  FERVIT_G_HEAD_LN_W,    /* mlp_head.0 | head.0 | norm  weight [E] */
+  FERVIT_G_HEAD_LN_B,
+  FERVIT_G_HEAD_W,       /* mlp_head.1 | head.2 | head  weight [C,E] */
+  FERVIT_G_HEAD_B,       /* [C] */
+  FERVIT_G_SPE_GROUP,    /* spe.group_embed.weight [3,Din] */
+  FERVIT_G_SPE_LAYER,    /* spe.layer_embed.weight [L,Din] */
+  FERVIT_G_LWN_GAMMA,    /* stack of lwn.norms.{l}.weight [L,Din] */
+  FERVIT_G_LWN_BETA,     /* stack of lwn.norms.{l}.bias   [L,Din] */
+  FERVIT_G_LWN_GATE,     /* lwn.gate [L] */
+  FERVIT_G_LEAM_W,       /* leam.layer_weights [L] */
+  FERVIT_G_SPE_GROUPS,   /* spe.groups int64 [L] (buffer, never a gradient) */
+  FERVIT_NUM_GLOBAL = 16
+};
+enum {
+  FERVIT_B_LN1_W = 0, FERVIT_B_LN1_B,
+  FERVIT_B_QKV_W,  /* attn.qkv.weight | self_attn.in_proj_weight [3E,E], rows [Q;K;V] */
+  FERVIT_B_QKV_B,
+  FERVIT_B_PROJ_W, /* attn.proj.weight | self_attn.out_proj.weight [E,E] */
+  FERVIT_B_PROJ_B,
+  FERVIT_B_LN2_W, FERVIT_B_LN2_B,
+  FERVIT_B_FC1_W,  /* mlp.fc1.weight | linear1.weight [F,E] */
+  FERVIT_B_FC1_B,
+  FERVIT_B_FC2_W,  /* mlp.fc2.weight | linear2.weight [E,F] */
+  FERVIT_B_FC2_B,
+  FERVIT_B_AD1_W,  /* adapters.{i}.adapter.0.weight [A,E] */
+  FERVIT_B_AD1_B,
+  FERVIT_B_AD2_W,  /* adapters.{i}.adapter.2.weight [E,A] */
+  FERVIT_B_AD2_B,
+  FERVIT_B_ALPHA,  /* adapters.{i}.alpha [1] */
+  FERVIT_NUM_BLOCK = 17
+};
+
+int fervit_plan_create(const fervit_config* cfg, fervit_plan** out);
+void fervit_plan_destroy(fervit_plan* plan);
+int fervit_plan_num_slots(const fervit_plan* plan);
+/* element count of a slot's parameter (0 when the configuration does not use it) */
+long long fervit_plan_slot_numel(const fervit_plan* plan, int slot);
+
+/* params[n]: device pointers of the fp32 parameters (NULL for unused slots). Pointers are borrowed: PyTorch
+ * owns the nn.Parameters (SURVEY.md §8b "Ownership"). */
+int fervit_plan_set_params(fervit_plan* plan, const void* const* params, int n);
+
+/* bf16 weight cache (W and W^T of every GEMM weight), a derived non-persistent copy that the caller owns and
+ * refreshes after the optimizer changed the fp32 masters. slots == NULL refreshes every cached weight. */
+long long fervit_plan_wcache_bytes(const fervit_plan* plan);
+int fervit_plan_set_wcache(fervit_plan* plan, void* ptr, long long bytes);
+int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n, void* stream);
+
+/* Activation workspace for batch B. save_for_backward = 0 gives the (smaller) inference workspace. */
+long long fervit_plan_workspace_bytes(const fervit_plan* plan, int B, int save_for_backward);
+
+/* logits[B,C] = model(x). training != 0 enables dropout (seeded by `seed`, counter-based, reproducible in
+ * backward) and keeps the activations backward needs in `ws`. */
+int fervit_plan_forward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
+                        int save_for_backward, unsigned long long seed, float* logits, void* stream);
+
+/* Backward from dlogits[B,C]. grads[n]: where each parameter's gradient is WRITTEN (not accumulated); NULL = not
+ * needed (frozen). The pass is cut into stages so a data-parallel host can all-reduce finished gradient buckets
+ * while earlier blocks are still running: stage 0 = head, stage 1+k = block depth-1-k, stage depth+1 = input
+ * projection / cls / pos / pre-modules. Run stages [stage_begin, stage_end) in increasing order. */
+int fervit_plan_num_stages(const fervit_plan* plan);
+int fervit_plan_backward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
+                         unsigned long long seed, const float* dlogits, float* const* grads, int n,
+                         int stage_begin, int stage_end, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Loss: nn.CrossEntropyLoss(weight, label_smoothing), mean reduction
+ * (train_hybrid_latent_vit.py:236-241, train_latent_vit.py:248-253). loss[1]; dlogits[B,C] = grad_scale * dloss/dlogits
+ * (may be NULL). den_in (device scalar, may be NULL) overrides sum_i w[y_i], e.g. the global-batch value under
+ * data parallelism. den_out may be NULL.
+ * -------------------------------------------------------------------------------------------- */
+int fervit_cross_entropy(const float* logits, const long long* labels, const float* weight, float label_smoothing,
+                         int B, int C, const float* den_in, float grad_scale, float* loss, float* dlogits,
+                         float* den_out, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Stand-alone pre-modules (modules/leam.py:31-40, modules/layer_wise_norm.py:35-50,
+ * modules/semantic_pe.py:36-48), fused; any subset via the use_* flags. fp32 in / fp32 out.
+ * scratch for backward: fervit_premodules_scratch_floats(B, L, D) floats.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct fervit_premodules {
+  int use_spe, use_lwn, use_lwn_res, use_leam;
+  const float* group_embed;   /* [3,D]  */
+  const float* layer_embed;   /* [L,D]  */
+  const long long* groups;    /* [L]    */
+  const float* gamma;         /* [L,D]  */
+  const float* beta;          /* [L,D]  */
+  const float* gate;          /* [L]    */
+  const float* leam_w;        /* [L]    */
+  float eps;
+} fervit_premodules;
+int fervit_premodules_forward(const fervit_premodules* p, const float* x, int B, int L, int D, float* y, void* stream);
+long long fervit_premodules_scratch_floats(int B, int L, int D);
+int fervit_premodules_backward(const fervit_premodules* p, const float* x, const float* dy, int B, int L, int D,
+                               float* dx, float* scratch, float* dgamma, float* dbeta, float* dlayer_embed,
+                               float* dgroup_embed, float* dgate, float* dleam, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Operator-level entry points (parity tests and micro-benchmarks call these; the plan uses the same kernels).
+ * act_dtype: FERVIT_F32 or FERVIT_BF16 for the buffers typed void*.
+ * -------------------------------------------------------------------------------------------- */
+
+/* y = act(x W^T + b) (+ residual): nn.Linear / F.linear. fp32 mode: x, W fp32; bf16 mode: x, W bf16 ([N,K]).
+ * out (act_dtype) and out_f32 may each be NULL; residual fp32 [M,N] may be NULL; pre (act_dtype, pre-activation) may
+ * be NULL. force_bn: 0 = auto, else 64/128/256 N tile of the tcgen05 kernel (ignored in fp32 mode). */
+int fervit_linear_forward(int act_dtype, const void* x, const void* W, const float* bias, const float* residual,
+                          int M, int N, int K, int act, void* out, float* out_f32, void* pre, int force_bn,
+                          void* stream);
+/* dW[N,K] = alpha * dY^T X  (dY [M,N], X [M,K], act_dtype): the weight gradient of nn.Linear.
+ * scratch: fervit_linear_wgrad_scratch_floats(M,N,K) floats. */
+long long fervit_linear_wgrad_scratch_floats(int M, int N, int K);
+int fervit_linear_wgrad(int act_dtype, const void* dY, const void* X, int M, int N, int K, float alpha, float* dW,
+                        float* scratch, void* stream);
+
+/* nn.LayerNorm over rows of fp32 x[rows,E]; y in act_dtype and/or fp32; mean/rstd [rows] saved for backward. */
+int fervit_layernorm_forward(int act_dtype, const float* x, const float* gamma, const float* beta, float eps, int rows,
+                             int E, float* y_f32, void* y_act, float* mean, float* rstd, void* stream);
+/* dx = LN'(dy) (+ dres). dy is act_dtype. dgamma/dbeta NULL = not needed.
+ * scratch: fervit_layernorm_scratch_floats(rows,E) floats when dgamma is requested. */
+long long fervit_layernorm_scratch_floats(int rows, int E);
+int fervit_layernorm_backward(int act_dtype, const void* dy, const float* x, const float* mean, const float* rstd,
+                              const float* gamma, const float* dres, int rows, int E, float* dx_f32, void* dx_act,
+                              float* scratch, float* dgamma, float* dbeta, void* stream);
+
+/* softmax(q k^T / sqrt(hd)) v per (sample, head): F.scaled_dot_product_attention / nn.MultiheadAttention core.
+ * qkv [B*S, 3*H*hd] columns [Q|K|V]; out [B*S, H*hd]; lse [B*H*S] (may be NULL in forward-only use). */
+int fervit_attention_forward(int act_dtype, const void* qkv, int B, int S, int H, int hd, float dropout_p,
+                             unsigned long long seed, unsigned int site, void* out, float* lse, void* stream);
+int fervit_attention_backward(int act_dtype, const void* qkv, const void* out, const void* dout, const float* lse,
+                              int B, int S, int H, int hd, float dropout_p, unsigned long long seed,
+                              unsigned int site, void* dqkv, void* stream);
+
+/* keep-mask scaled by 1/(1-p) of dropout site `site` for n elements (tests feed it to the oracle) */
+int fervit_dropout_mask(float* out, long long n, float p, unsigned long long seed, unsigned int site, void* stream);
+/* site ids used by the plan: block b has sites 8*b + {0: attention weights, 1: after out-proj, 2: after the MLP
+ * activation, 3: after fc2}; input dropout and head dropout use the two ids below. */
+#define FERVIT_SITE_INPUT 0xFFFF0u
+#define FERVIT_SITE_HEAD 0xFFFF1u
+
+/* fp32 -> bf16 cast (n multiple of 4) */
+int fervit_cast_bf16(const float* src, void* dst, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FERVIT_B200_H_ */
