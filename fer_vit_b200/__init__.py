@@ -1,0 +1,12 @@
+"""fer_vit_b200 — B200-native (sm_100a) train-step path of FER-ViT's LatentViT / HybridLatentViT / ImageViT."""
+from .native_module import set_default_precision, get_default_precision
+from .runtime import CrossEntropyLoss, cross_entropy
+from .models_fer_vit import (LatentViT, LatentViTv2, HybridLatentViT, AdapterModule, create_hybrid_latent_vit,
+                             RECOMMENDED_STRATEGIES, ImageViT, PatchEmbedding, create_vit_tiny, create_vit_small,
+                             create_vit_base)
+from .modules import LEAM, SemanticPE, LayerWiseNorm
+
+__all__ = ["set_default_precision", "get_default_precision", "CrossEntropyLoss", "cross_entropy", "LatentViT",
+           "LatentViTv2", "HybridLatentViT", "AdapterModule", "create_hybrid_latent_vit", "RECOMMENDED_STRATEGIES",
+           "ImageViT", "PatchEmbedding", "create_vit_tiny", "create_vit_small", "create_vit_base", "LEAM",
+           "SemanticPE", "LayerWiseNorm"]

@@ -76,7 +76,7 @@ __global__ void attn_fwd_kernel(const AT* __restrict__ qkv, AT* __restrict__ out
     const float pj = __expf(s - m);
     l += pj;
     float pw = pj;
-    if (drop.threshold) pw = drop_keep(drop.seed, drop.site, drop_base + j, drop.threshold) ? pj * drop.scale : 0.f;
+    if (drop.threshold) pw = drop_keep(drop.eff(), drop.site, drop_base + j, drop.threshold) ? pj * drop.scale : 0.f;
     const float* vj = Vs + j * LD;
 #pragma unroll
     for (int d = 0; d < HD; d += 4) {
@@ -162,7 +162,7 @@ __global__ void attn_bwd_kernel(const AT* __restrict__ qkv, const AT* __restrict
         dp += (ov.x * vv.x + ov.y * vv.y) + (ov.z * vv.z + ov.w * vv.w);
       }
       const float pij = __expf(s * scale - li);
-      if (drop.threshold) dp = drop_keep(drop.seed, drop.site, drop_base + j, drop.threshold) ? dp * drop.scale : 0.f;
+      if (drop.threshold) dp = drop_keep(drop.eff(), drop.site, drop_base + j, drop.threshold) ? dp * drop.scale : 0.f;
       const float ds = pij * (dp - di) * scale;
 #pragma unroll
       for (int d = 0; d < HD; d += 4) {
@@ -198,7 +198,7 @@ __global__ void attn_bwd_kernel(const AT* __restrict__ qkv, const AT* __restrict
       const float prj = __expf(s * scale - Ls[r]);
       float pt = prj;
       if (drop.threshold) {
-        const bool keep = drop_keep(drop.seed, drop.site, ((uint64_t)bh * S + r) * S + j, drop.threshold);
+        const bool keep = drop_keep(drop.eff(), drop.site, ((uint64_t)bh * S + r) * S + j, drop.threshold);
         pt = keep ? prj * drop.scale : 0.f;
         dp = keep ? dp * drop.scale : 0.f;
       }

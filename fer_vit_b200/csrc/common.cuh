@@ -99,13 +99,18 @@ static inline uint32_t drop_threshold(float p) {
 
 struct Dropout {       // passed by value to kernels; p == 0 disables
   uint64_t seed;
+  // optional device-resident counter added to `seed`: lets a captured CUDA graph draw a fresh mask per replay
+  const unsigned long long* seed_ptr;
   uint32_t site;
   uint32_t threshold;  // 0 = off
   float scale;         // 1/(1-p)
+  __device__ __forceinline__ uint64_t eff() const { return seed_ptr ? seed + (uint64_t)(*seed_ptr) : seed; }
 };
-static inline Dropout make_dropout(float p, uint64_t seed, uint32_t site) {
+static inline Dropout make_dropout(float p, uint64_t seed, uint32_t site,
+                                   const unsigned long long* seed_ptr = nullptr) {
   Dropout d;
   d.seed = seed;
+  d.seed_ptr = seed_ptr;
   d.site = site;
   d.threshold = (p > 0.f) ? drop_threshold(p) : 0u;
   d.scale = (p > 0.f) ? 1.0f / (1.0f - p) : 1.0f;

@@ -68,7 +68,7 @@ __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __re
     float v = cls[c] + pos[c];
     if (drop.threshold) {
       const uint64_t idx = (uint64_t)b * S * E + c;
-      v = drop_keep(drop.seed, drop.site, idx, drop.threshold) ? v * drop.scale : 0.f;
+      v = drop_keep(drop.eff(), drop.site, idx, drop.threshold) ? v * drop.scale : 0.f;
     }
     x0[(size_t)b * S * E + c] = v;
     if (x0_at) x0_at[(size_t)b * S * E + c] = from_f32<AT>(v);
@@ -82,7 +82,7 @@ __global__ void token_dropout_kernel(float* __restrict__ x0, AT* __restrict__ x0
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int s = (int)((i / E) % S);
     if (s == 0) continue;
-    const float v = drop_keep(drop.seed, drop.site, i, drop.threshold) ? x0[i] * drop.scale : 0.f;
+    const float v = drop_keep(drop.eff(), drop.site, i, drop.threshold) ? x0[i] * drop.scale : 0.f;
     x0[i] = v;
     if (x0_at) x0_at[i] = from_f32<AT>(v);
   }
@@ -103,10 +103,10 @@ __global__ void gather_tokens_kernel(const float* __restrict__ dx0, AT* __restri
     const size_t src = (b * S + 1 + l) * E + c;
     float4 v = *reinterpret_cast<const float4*>(dx0 + src);
     if (drop.threshold) {
-      v.x = drop_keep(drop.seed, drop.site, src + 0, drop.threshold) ? v.x * drop.scale : 0.f;
-      v.y = drop_keep(drop.seed, drop.site, src + 1, drop.threshold) ? v.y * drop.scale : 0.f;
-      v.z = drop_keep(drop.seed, drop.site, src + 2, drop.threshold) ? v.z * drop.scale : 0.f;
-      v.w = drop_keep(drop.seed, drop.site, src + 3, drop.threshold) ? v.w * drop.scale : 0.f;
+      v.x = drop_keep(drop.eff(), drop.site, src + 0, drop.threshold) ? v.x * drop.scale : 0.f;
+      v.y = drop_keep(drop.eff(), drop.site, src + 1, drop.threshold) ? v.y * drop.scale : 0.f;
+      v.z = drop_keep(drop.eff(), drop.site, src + 2, drop.threshold) ? v.z * drop.scale : 0.f;
+      v.w = drop_keep(drop.eff(), drop.site, src + 3, drop.threshold) ? v.w * drop.scale : 0.f;
     }
     store4<AT>(out + e, v);
   }
@@ -124,7 +124,7 @@ __global__ void colsum_partial_kernel(const T* __restrict__ in, int R, int C, lo
   for (int r = r0; r < r1; ++r) {
     float v = to_f32<T>(in[(size_t)r * ld + c]);
     if (drop.threshold)
-      v = drop_keep(drop.seed, drop.site, (uint64_t)r * ld + c, drop.threshold) ? v * drop.scale : 0.f;
+      v = drop_keep(drop.eff(), drop.site, (uint64_t)r * ld + c, drop.threshold) ? v * drop.scale : 0.f;
     s += v;
   }
   partial[(size_t)blockIdx.y * C + c] = s;
@@ -209,7 +209,7 @@ __global__ void adapter_finalize_kernel(const float* __restrict__ part, int npar
 
 __global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, Dropout drop) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = drop_keep(drop.seed, drop.site, i, drop.threshold) ? drop.scale : 0.f;
+    out[i] = drop_keep(drop.eff(), drop.site, i, drop.threshold) ? drop.scale : 0.f;
 }
 
 __global__ void fill_kernel(float* __restrict__ out, size_t n, float v) {

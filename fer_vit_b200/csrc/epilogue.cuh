@@ -42,7 +42,7 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
     const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
-      v[i] = drop_keep(e.drop.seed, e.drop.site, base + i, e.drop.threshold) ? v[i] * e.drop.scale : 0.0f;
+      v[i] = drop_keep(e.drop.eff(), e.drop.site, base + i, e.drop.threshold) ? v[i] * e.drop.scale : 0.0f;
   }
   int orow = row;
   int prow = 0;

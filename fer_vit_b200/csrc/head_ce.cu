@@ -59,7 +59,7 @@ head_fwd_kernel(const float* __restrict__ x, int B, int S, int E, const float* _
       if (drop.threshold) {
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          hv[t] = drop_keep(drop.seed, drop.site, (uint64_t)b * E + c + t, drop.threshold) ? hv[t] * drop.scale : 0.f;
+          hv[t] = drop_keep(drop.eff(), drop.site, (uint64_t)b * E + c + t, drop.threshold) ? hv[t] * drop.scale : 0.f;
       }
 #pragma unroll
       for (int k = 0; k < MAXC; ++k) {
@@ -112,7 +112,7 @@ head_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dlogit
       if (drop.threshold) {
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-          dn[t] = drop_keep(drop.seed, drop.site, (uint64_t)b * E + c + t, drop.threshold) ? dn[t] * drop.scale : 0.f;
+          dn[t] = drop_keep(drop.eff(), drop.site, (uint64_t)b * E + c + t, drop.threshold) ? dn[t] * drop.scale : 0.f;
       }
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -166,7 +166,7 @@ head_wgrad_partial_kernel(const float* __restrict__ x, const float* __restrict__
   for (int b = b0; b < b1; ++b) {
     const float xh = (x[(size_t)b * S * E + e] - mean[b]) * rstd[b];
     float m = 1.f;
-    if (drop.threshold) m = drop_keep(drop.seed, drop.site, (uint64_t)b * E + e, drop.threshold) ? drop.scale : 0.f;
+    if (drop.threshold) m = drop_keep(drop.eff(), drop.site, (uint64_t)b * E + e, drop.threshold) ? drop.scale : 0.f;
     const float h = (xh * g + be) * m;
     float dn = 0.f;
 #pragma unroll

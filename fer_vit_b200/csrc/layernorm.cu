@@ -122,10 +122,10 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
           if (at_drop.threshold) {
             // the activation-dtype copy feeds the dgrad/wgrad of a sub-layer whose output went through dropout
             const uint64_t base = (uint64_t)row * E + c;
-            o.x = drop_keep(at_drop.seed, at_drop.site, base + 0, at_drop.threshold) ? o.x * at_drop.scale : 0.f;
-            o.y = drop_keep(at_drop.seed, at_drop.site, base + 1, at_drop.threshold) ? o.y * at_drop.scale : 0.f;
-            o.z = drop_keep(at_drop.seed, at_drop.site, base + 2, at_drop.threshold) ? o.z * at_drop.scale : 0.f;
-            o.w = drop_keep(at_drop.seed, at_drop.site, base + 3, at_drop.threshold) ? o.w * at_drop.scale : 0.f;
+            o.x = drop_keep(at_drop.eff(), at_drop.site, base + 0, at_drop.threshold) ? o.x * at_drop.scale : 0.f;
+            o.y = drop_keep(at_drop.eff(), at_drop.site, base + 1, at_drop.threshold) ? o.y * at_drop.scale : 0.f;
+            o.z = drop_keep(at_drop.eff(), at_drop.site, base + 2, at_drop.threshold) ? o.z * at_drop.scale : 0.f;
+            o.w = drop_keep(at_drop.eff(), at_drop.site, base + 3, at_drop.threshold) ? o.w * at_drop.scale : 0.f;
           }
           store4<AT>(dx_at + (size_t)row * E + c, o);
         }

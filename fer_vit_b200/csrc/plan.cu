@@ -267,10 +267,11 @@ struct Ctx {
   const fervit_plan* p;
   cudaStream_t st;
   bool training;
+  const unsigned long long* seed_dev;
   uint64_t seed;
   Dropout site(int blk, int k) const {
     const float pr = training ? p->cfg.dropout : 0.f;
-    return make_dropout(pr, seed, (uint32_t)(blk * 8 + k));
+    return make_dropout(pr, seed, (uint32_t)(blk * 8 + k), seed_dev);
   }
   Dropout none() const { return make_dropout(0.f, 0, 0); }
 };
@@ -330,14 +331,14 @@ PreParams pre_params(const fervit_plan* p) {
 
 template <typename AT>
 int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_bytes, bool training, bool save,
-                 uint64_t seed, float* logits, cudaStream_t st) {
+                 uint64_t seed, const unsigned long long* seed_dev, float* logits, cudaStream_t st) {
   const fervit_config& c = p->cfg;
   constexpr bool F32 = std::is_same<AT, float>::value;
   Arena ar{reinterpret_cast<char*>(ws), 0};
   Bufs b;
   carve<AT>(p, B, save, ar, b);
   FV_CHECK((long long)ar.off <= ws_bytes, "forward: workspace too small (%lld < %zu bytes)", ws_bytes, ar.off);
-  Ctx cx{p, st, training, seed};
+  Ctx cx{p, st, training, seed_dev, seed};
   const int S = p->S, T = B * S, Tl = B * c.L, E = c.E, F = c.F, A = c.adapter_dim;
   const bool post = !c.norm_first;
 
@@ -365,7 +366,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
     e.out_f32 = b.x[0];
     if (post && !F32) e.out = b.x_at[0];
     FV_TRY(linear<AT>(cx, a_in, Tl, FERVIT_G_IN_W, false, e));
-    const Dropout din = make_dropout((training && c.input_dropout) ? c.dropout : 0.f, seed, FERVIT_SITE_INPUT);
+    const Dropout din = make_dropout((training && c.input_dropout) ? c.dropout : 0.f, seed, FERVIT_SITE_INPUT, seed_dev);
     FV_TRY(cls_rows<AT>(p->P(FERVIT_G_CLS), p->P(FERVIT_G_POS), b.x[0], (post && !F32) ? (AT*)b.x_at[0] : nullptr, B, S,
                         E, din, st));
     FV_TRY(token_dropout<AT>(b.x[0], (post && !F32) ? (AT*)b.x_at[0] : nullptr, B, S, E, din, st));
@@ -430,7 +431,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
   }
 
   // ---------------- head ----------------
-  const Dropout dh = make_dropout(training ? c.head_dropout : 0.f, seed, FERVIT_SITE_HEAD);
+  const Dropout dh = make_dropout(training ? c.head_dropout : 0.f, seed, FERVIT_SITE_HEAD, seed_dev);
   FV_TRY(head_fwd(b.x[c.depth], B, S, E, p->P(FERVIT_G_HEAD_LN_W), p->P(FERVIT_G_HEAD_LN_B), c.eps_head,
                   p->P(FERVIT_G_HEAD_W), p->P(FERVIT_G_HEAD_B), c.C, dh, logits, b.head_mean, b.head_rstd, st));
   return 0;
@@ -438,6 +439,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
 
 template <typename AT>
 int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_bytes, bool training, uint64_t seed,
+                  const unsigned long long* seed_dev,
                   const float* dlogits, float* const* G, int stage_begin, int stage_end, cudaStream_t st) {
   const fervit_config& c = p->cfg;
   constexpr bool F32 = std::is_same<AT, float>::value;
@@ -445,7 +447,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   Bufs b;
   carve<AT>(p, B, true, ar, b);
   FV_CHECK((long long)ar.off <= ws_bytes, "backward: workspace too small (%lld < %zu bytes)", ws_bytes, ar.off);
-  Ctx cx{p, st, training, seed};
+  Ctx cx{p, st, training, seed_dev, seed};
   const int S = p->S, T = B * S, Tl = B * c.L, E = c.E, F = c.F, A = c.adapter_dim;
   const bool post = !c.norm_first;
   auto GB = [&](int blk, int s) -> float* { return G[p->bslot(blk, s)]; };
@@ -455,7 +457,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
     if (stage == 0) {
       // ---------------- head ----------------
       p->bwd_cur = 0;
-      const Dropout dh = make_dropout(training ? c.head_dropout : 0.f, seed, FERVIT_SITE_HEAD);
+      const Dropout dh = make_dropout(training ? c.head_dropout : 0.f, seed, FERVIT_SITE_HEAD, seed_dev);
       const int wg = G[FERVIT_G_HEAD_W] != nullptr;
       if (wg)
         FV_CHECK(G[FERVIT_G_HEAD_B] && G[FERVIT_G_HEAD_LN_W] && G[FERVIT_G_HEAD_LN_B],
@@ -632,7 +634,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
     } else {
       // ---------------- input stage ----------------
       const int cur = p->bwd_cur;
-      const Dropout din = make_dropout((training && c.input_dropout) ? c.dropout : 0.f, seed, FERVIT_SITE_INPUT);
+      const Dropout din = make_dropout((training && c.input_dropout) ? c.dropout : 0.f, seed, FERVIT_SITE_INPUT, seed_dev);
       if (G[FERVIT_G_POS]) {
         FV_TRY(colsum<float>(b.dx[cur], B, S * E, (long long)S * E, b.scratch, nullptr, 1.0f, G[FERVIT_G_POS], din, st));
         if (G[FERVIT_G_CLS])
@@ -785,28 +787,30 @@ FV_API long long fervit_plan_workspace_bytes(const fervit_plan* plan, int B, int
 }
 
 FV_API int fervit_plan_forward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
-                               int save_for_backward, unsigned long long seed, float* logits, void* stream) {
+                               int save_for_backward, unsigned long long seed, const unsigned long long* seed_dev,
+                               float* logits, void* stream) {
   FV_CHECK(plan && x && ws && logits, "forward: null argument");
   FV_CHECK(B > 0, "forward: empty batch");
   FV_CHECK(((uintptr_t)ws & 255) == 0, "forward: workspace must be 256-byte aligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (plan->cfg.mode == FERVIT_BF16) {
     FV_CHECK(plan->wcache != nullptr, "forward: bf16 mode needs the weight cache (set_wcache + refresh_wcache)");
-    return forward_impl<bf16>(plan, x, B, ws, ws_bytes, training != 0, save_for_backward != 0, seed, logits, st);
+    return forward_impl<bf16>(plan, x, B, ws, ws_bytes, training != 0, save_for_backward != 0, seed, seed_dev, logits, st);
   }
-  return forward_impl<float>(plan, x, B, ws, ws_bytes, training != 0, save_for_backward != 0, seed, logits, st);
+  return forward_impl<float>(plan, x, B, ws, ws_bytes, training != 0, save_for_backward != 0, seed, seed_dev, logits, st);
 }
 
 FV_API int fervit_plan_num_stages(const fervit_plan* plan) { return plan ? plan->cfg.depth + 2 : 0; }
 
 FV_API int fervit_plan_backward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
-                                unsigned long long seed, const float* dlogits, float* const* grads, int n,
+                                unsigned long long seed, const unsigned long long* seed_dev, const float* dlogits,
+                                float* const* grads, int n,
                                 int stage_begin, int stage_end, void* stream) {
   FV_CHECK(plan && x && ws && dlogits && grads, "backward: null argument");
   FV_CHECK(n == plan->nslots(), "backward: expected %d gradient slots, got %d", plan->nslots(), n);
   FV_CHECK(stage_begin >= 0 && stage_end <= plan->cfg.depth + 2 && stage_begin <= stage_end, "backward: bad stage range");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (plan->cfg.mode == FERVIT_BF16)
-    return backward_impl<bf16>(plan, x, B, ws, ws_bytes, training != 0, seed, dlogits, grads, stage_begin, stage_end, st);
-  return backward_impl<float>(plan, x, B, ws, ws_bytes, training != 0, seed, dlogits, grads, stage_begin, stage_end, st);
+    return backward_impl<bf16>(plan, x, B, ws, ws_bytes, training != 0, seed, seed_dev, dlogits, grads, stage_begin, stage_end, st);
+  return backward_impl<float>(plan, x, B, ws, ws_bytes, training != 0, seed, seed_dev, dlogits, grads, stage_begin, stage_end, st);
 }

@@ -132,10 +132,13 @@ int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n, void*
 /* Activation workspace for batch B. save_for_backward = 0 gives the (smaller) inference workspace. */
 long long fervit_plan_workspace_bytes(const fervit_plan* plan, int B, int save_for_backward);
 
-/* logits[B,C] = model(x). training != 0 enables dropout (seeded by `seed`, counter-based, reproducible in
- * backward) and keeps the activations backward needs in `ws`. */
+/* logits[B,C] = model(x). training != 0 enables dropout; save_for_backward != 0 keeps the activations backward
+ * needs in `ws`. Dropout is counter-based: keep(seed + *seed_dev, site, element) is a pure function, so backward
+ * recomputes the masks from the same (seed, seed_dev). seed_dev (device scalar, may be NULL) lets a captured CUDA
+ * graph draw fresh masks on every replay by bumping one device counter. */
 int fervit_plan_forward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
-                        int save_for_backward, unsigned long long seed, float* logits, void* stream);
+                        int save_for_backward, unsigned long long seed, const unsigned long long* seed_dev,
+                        float* logits, void* stream);
 
 /* Backward from dlogits[B,C]. grads[n]: where each parameter's gradient is WRITTEN (not accumulated); NULL = not
  * needed (frozen). The pass is cut into stages so a data-parallel host can all-reduce finished gradient buckets
@@ -143,8 +146,8 @@ int fervit_plan_forward(fervit_plan* plan, const float* x, int B, void* ws, long
  * projection / cls / pos / pre-modules. Run stages [stage_begin, stage_end) in increasing order. */
 int fervit_plan_num_stages(const fervit_plan* plan);
 int fervit_plan_backward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
-                         unsigned long long seed, const float* dlogits, float* const* grads, int n,
-                         int stage_begin, int stage_end, void* stream);
+                         unsigned long long seed, const unsigned long long* seed_dev, const float* dlogits,
+                         float* const* grads, int n, int stage_begin, int stage_end, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
  * Loss: nn.CrossEntropyLoss(weight, label_smoothing), mean reduction

@@ -1,0 +1,288 @@
+"""GPU: whole-model parity of the drop-in classes (through the C-ABI plan) against
+  (a) the golden vectors produced by the UNMODIFIED reference classes (tests/golden/*.npz), and
+  (b) the oracle run live on the same seeded inputs at the reference's real widths,
+plus size-independent properties at BASELINE.json's full batch sizes.
+
+Gates (BASELINE.json north_star): logits and every gradient within 1e-4 (fp32 mode) / 2e-2 (bf16 mode) norm-wise
+relative error, identical top-1 predictions.
+"""
+import pytest
+import torch
+
+from tests.test_gpu_ops import record
+from tests.util import FIXTURES, build_model, load_golden, oracle_forward, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def step(model, x, y, weight=None, smoothing=0.0):
+    import fer_vit_b200 as fv
+    model.zero_grad(set_to_none=True)
+    logits = model(x)
+    loss = fv.cross_entropy(logits, y, weight, smoothing)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return logits.detach(), loss.detach(), grads
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", FIXTURES)
+def test_model_matches_reference_golden(name, precision):
+    g = load_golden(name)
+    model = build_model(name, precision)
+    model.load_state_dict(g["sd"], strict=True)          # same keys / shapes as the reference checkpoint
+    model = model.cuda()
+    # the Hybrid fixtures were generated in eval() (its head Dropout(0.1) is hard-coded); the others in train()
+    model.train(not name.startswith("hybrid"))
+    w = g["class_weight"].cuda() if g["class_weight"] is not None else None
+    logits, loss, grads = step(model, g["x"].cuda(), g["y"].cuda(), w, g["label_smoothing"])
+    tol = TOL[precision]
+    e_l = relerr(logits, g["logits"])
+    errs = {k: relerr(grads[k], g["grad"][k]) for k in g["grad"]}
+    worst = max(errs, key=errs.get)
+    record("model_vs_golden", fixture=name, precision=precision, err_logits=e_l,
+           err_loss=abs(loss.item() - float(g["loss"])), worst_grad=errs[worst], worst_key=worst)
+    assert set(grads) == set(g["grad"]), set(grads) ^ set(g["grad"])
+    assert e_l < tol, e_l
+    assert errs[worst] < tol, (worst, errs[worst])
+    assert abs(loss.item() - float(g["loss"])) < tol * max(1.0, abs(float(g["loss"])))
+    if precision == "fp32":
+        assert torch.equal(logits.argmax(-1).cpu(), g["logits"].argmax(-1))
+
+
+def _oracle_step(fwd, sd, x, y, masks=None, weight=None, smoothing=0.0):
+    from oracle import reference_math as R
+    logits = fwd(sd, x, masks)
+    loss = R.cross_entropy(logits, y, weight, smoothing)
+    return logits.detach(), loss.detach(), R.grads_of(loss, sd)
+
+
+def _compare(tag, precision, got, ref, extra=None):
+    logits, loss, grads = got
+    rl, rloss, rg = ref
+    e_l = relerr(logits, rl)
+    errs = {k: relerr(grads[k], rg[k]) for k in rg}
+    worst = max(errs, key=errs.get)
+    record(tag, precision=precision, err_logits=e_l, err_loss=abs(loss.item() - rloss.item()), worst_grad=errs[worst],
+           worst_key=worst, **(extra or {}))
+    tol = TOL[precision]
+    assert set(grads) == set(rg)
+    assert e_l < tol, e_l
+    assert errs[worst] < tol, (worst, errs[worst])
+    # top-1 must agree wherever the reference's top-2 margin exceeds the logit tolerance
+    top2 = rl.float().topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 4 * tol * rl.abs().max()
+    assert torch.equal(logits.argmax(-1).cpu()[clear], rl.argmax(-1)[clear])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_hybrid_vit_base_adapter_vs_oracle(precision):
+    """BASELINE config 3 shape: frozen ViT-B/16 blocks + Adapter(64) on 18x512 w+ tokens (reduced batch for the CPU oracle)."""
+    import fer_vit_b200 as fv
+    from oracle import baseline_models as BM
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    sd = BM.hybrid_state_dict(seed=3)
+    for i in range(12):
+        sd[f"adapters.{i}.alpha"] = torch.ones(1) * (0.1 + 0.02 * i)
+    model = fv.create_hybrid_latent_vit(model_size="base", use_pretrained=False, freeze_transformer=True,
+                                        use_adapter=True, adapter_dim=64)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(11)
+    B = 8
+    # second input distribution of SURVEY.md 8d: non-zero mean, like real pSp latents (stresses LayerNorm)
+    x = 0.5 * torch.randn(B, 18, 512, generator=g) + 0.3 * torch.randn(1, 18, 512, generator=g)
+    y = torch.randint(0, 7, (B,), generator=g)
+    BM.hybrid_trainable(sd)
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, 12, True, m), sd, x, y)
+    got = step(model, x.cuda(), y.cuda())
+    assert sum(v.numel() for v in got[2].values()) == 1_605_907      # trainable set of SURVEY.md 8a row a7
+    _compare("hybrid_vitb_adapter_vs_oracle", precision, got, ref, {"B": B})
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_hybrid_head_dropout_train_mode(precision):
+    """train(): the head's Dropout(0.1) is active; the oracle receives the very mask the kernel drew."""
+    from fer_vit_b200 import _lib as L
+    from oracle import reference_math as R
+    g = load_golden("hybrid_adapter")
+    model = build_model("hybrid_adapter", precision)
+    model.load_state_dict(g["sd"], strict=True)
+    model = model.cuda().train()
+    runner = model.plan_runner()
+    runner._next_seed = lambda training: 4242
+    x, y = g["x"], g["y"]
+    got = step(model, x.cuda(), y.cuda())
+    B, E = x.shape[0], 64
+    mask = torch.empty(B * E, device="cuda")
+    L.check(L.lib().fervit_dropout_mask(mask.data_ptr(), B * E, 0.1, 4242, L.SITE_HEAD, torch.cuda.current_stream().cuda_stream))
+    masks = {"head": mask.reshape(B, E).cpu().double()}
+    sd = {k: (v.double().requires_grad_(k in g["grad"]) if v.is_floating_point() else v) for k, v in g["sd"].items()}
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 2, 2, True, m), sd, x.double(), y, masks)
+    assert (masks["head"] == 0).any()
+    _compare("hybrid_head_dropout", precision, got, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_latent_vit_default_config_vs_oracle(precision):
+    """BASELINE config 1: LatentViT 512/d6/h8/2048 on 18x512 tokens, batch 32."""
+    import fer_vit_b200 as fv
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    torch.manual_seed(5)
+    model = fv.LatentViT(dropout=0.0)
+    with torch.no_grad():                         # de-correlate the deep-copied layers, shrink randn cls/pos
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+        for i, layer in enumerate(model.transformer.layers):
+            for p in layer.parameters():
+                if p.dim() > 1:
+                    p.add_(0.02 * torch.randn_like(p))
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(32, 18, 512, generator=g); y = torch.randint(0, 7, (32,), generator=g)
+    ref = _oracle_step(lambda s, xx, m: R.latent_vit_forward(s, xx, 6, 8, m), sd, x, y, smoothing=0.1)
+    model = model.cuda().train()
+    import fer_vit_b200 as fv2
+    model.zero_grad(set_to_none=True)
+    logits = model(x.cuda())
+    loss = fv2.cross_entropy(logits, y.cuda(), None, 0.1)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_latent_vit_dropout_masks_vs_oracle(precision):
+    """dropout = 0.1 in train(): all four per-layer sites (attention weights, after out-proj, after ReLU, after
+    linear2) use counter-based masks that the test materialises and hands to the oracle."""
+    import fer_vit_b200 as fv
+    from fer_vit_b200 import _lib as L
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    torch.manual_seed(9)
+    E, H, F, depth, B, S = 64, 2, 128, 2, 5, 19
+    model = fv.LatentViT(latent_dim=64, embed_dim=E, depth=depth, heads=H, mlp_dim=F, dropout=0.1)
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in model.state_dict().items()}
+    model = model.cuda().train()
+    runner = model.plan_runner()
+    runner._next_seed = lambda training: 99
+    x = torch.randn(B, 18, 64); y = torch.randint(0, 7, (B,))
+    got = step(model, x.cuda(), y.cuda())
+
+    def mask(n, site, shape):
+        m = torch.empty(n, device="cuda")
+        L.check(L.lib().fervit_dropout_mask(m.data_ptr(), n, 0.1, 99, site, torch.cuda.current_stream().cuda_stream))
+        return m.reshape(shape).cpu().double()
+    masks = {}
+    for i in range(depth):
+        masks[("attn", i)] = mask(B * H * S * S, 8 * i + 0, (B, H, S, S))
+        masks[("drop1", i)] = mask(B * S * E, 8 * i + 1, (B, S, E))
+        masks[("ffn", i)] = mask(B * S * F, 8 * i + 2, (B, S, F))
+        masks[("drop2", i)] = mask(B * S * E, 8 * i + 3, (B, S, E))
+    ref = _oracle_step(lambda s, xx, m: R.latent_vit_forward(s, xx, depth, H, m), sd, x.double(), y, masks)
+    _compare("latent_vit_dropout", precision, got, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_latent_vit_v2_config4_vs_oracle(precision):
+    """BASELINE config 4 shape: LatentViTv2 with LEAM + SemanticPE + LayerWiseNorm(residual) (reduced batch)."""
+    import fer_vit_b200 as fv
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    torch.manual_seed(6)
+    model = fv.LatentViTv2(dropout=0.0, use_lwn=True, use_lwn_residual=True, use_spe=True, use_leam=True)
+    with torch.no_grad():
+        model.lwn.gate.add_(4.0 + torch.randn(18))
+        for p in model.parameters():
+            if p.dim() == 1 and p.numel() > 18:
+                p.add_(0.05 * torch.randn_like(p))
+    sd = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v.clone())
+          for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(43)
+    B = 16
+    x = 0.6 * torch.randn(B, 18, 512, generator=g) + 0.2; y = torch.randint(0, 7, (B,), generator=g)
+    ref = _oracle_step(lambda s, xx, m: R.latent_vit_v2_forward(s, xx, 6, 8, True, True, True, True, m), sd, x, y)
+    got = step(model.cuda().train(), x.cuda(), y.cuda())
+    _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_image_vit_config2_vs_oracle(precision):
+    """BASELINE config 2 shape: ImageViT 512/d6/h8/2048 on 224x224 (S = 197), reduced batch."""
+    import fer_vit_b200 as fv
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    torch.manual_seed(7)
+    model = fv.ImageViT(embed_dim=512, depth=6, heads=8, mlp_dim=2048, dropout=0.0)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.05 * torch.randn_like(p))
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(44)
+    B = 3
+    x = torch.randn(B, 3, 224, 224, generator=g); y = torch.randint(0, 7, (B,), generator=g)
+    ref = _oracle_step(lambda s, xx, m: R.image_vit_forward(s, xx, 6, 8, 16, m), sd, x, y)
+    got = step(model.cuda().train(), x.cuda(), y.cuda())
+    _compare("image_vit_cfg2_vs_oracle", precision, got, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_batch_properties_config3(precision):
+    """Size-independent properties at BASELINE config 3's full size (ViT-B + adapters, batch 256):
+    samples are independent, so the logits of a batch equal bit-for-bit the logits of its halves, and the
+    mean-loss gradient of the batch is the average of the halves' gradients."""
+    import fer_vit_b200 as fv
+    fv.set_default_precision(precision)
+    torch.manual_seed(8)
+    model = fv.create_hybrid_latent_vit(model_size="base", use_pretrained=False, freeze_transformer=True,
+                                        use_adapter=True, adapter_dim=64).cuda().eval()
+    B = 256
+    x = torch.randn(B, 18, 512, device="cuda"); y = torch.randint(0, 7, (B,), device="cuda")
+    full = step(model, x, y)
+    a = step(model, x[:128].contiguous(), y[:128].contiguous())
+    b = step(model, x[128:].contiguous(), y[128:].contiguous())
+    assert torch.equal(full[0], torch.cat([a[0], b[0]])), "logits must not depend on batch composition"
+    worst = 0.0
+    for k in full[2]:
+        worst = max(worst, relerr(full[2][k], 0.5 * (a[2][k] + b[2][k])))
+    record("full_batch_properties_cfg3", precision=precision, worst_grad_additivity=worst)
+    assert worst < (1e-4 if precision == "fp32" else 5e-3)
+    assert torch.isfinite(full[1]) and all(torch.isfinite(v).all() for v in full[2].values())
+
+
+def test_no_cpu_fallback():
+    import fer_vit_b200 as fv
+    model = build_model("latent_vit", "fp32")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(torch.randn(2, 18, 64))
+
+
+def test_inference_and_checkpoint_roundtrip(tmp_path):
+    """evaluate_model.py-style use: save a checkpoint, rebuild from config, strict load, no_grad eval forward."""
+    import fer_vit_b200 as fv
+    model = build_model("hybrid_adapter", "fp32").cuda().eval()
+    x = torch.randn(9, 18, 64, device="cuda")
+    with torch.no_grad():
+        a = model(x)
+    path = tmp_path / "ckpt.pt"
+    torch.save({"model_state_dict": model.state_dict()}, path)
+    again = build_model("hybrid_adapter", "fp32")
+    again.load_state_dict(torch.load(path)["model_state_dict"], strict=True)
+    again = again.cuda().eval()
+    with torch.no_grad():
+        b = again(x)
+    assert torch.equal(a, b)
+    assert not any(k.startswith("_") for k in model.state_dict())
+    # in-place optimizer updates invalidate the bf16 weight cache
+    again.precision = "bf16"
+    with torch.no_grad():
+        c = again(x)
+        again.input_proj.weight.mul_(2.0)
+        d = again(x)
+    assert relerr(c, a) < 2e-2 and relerr(d, c) > 1e-3

@@ -1,0 +1,281 @@
+"""GPU: operator-level parity of the C-ABI kernels against elementary torch arithmetic on the same inputs.
+
+Tolerances: fp32 kernels 1e-5 norm-wise relative (BASELINE.json fp32 gate is 1e-4 end to end); bf16 kernels are
+compared with a reference computed in fp32 from the SAME bf16-rounded inputs, so only accumulation order and the
+bf16 rounding of the output differ: 4e-3 norm-wise (bf16 has 8 mantissa bits: 2^-9 = 2e-3 per rounding).
+"""
+import ctypes as C
+import json
+import math
+import os
+
+import pytest
+import torch
+
+from tests.util import relerr
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def record(name, **vals):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_metrics.jsonl"), "a") as fh:
+        fh.write(json.dumps({"test": name, **vals}) + "\n")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fer_vit_b200 import _lib as L
+    assert torch.cuda.is_available()
+    return L
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+def gelu(x):
+    return 0.5 * x * (1 + torch.erf(x / math.sqrt(2)))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def run_linear(L, dtype, x, W, bias, residual, act, want_out, want_f32, want_pre, force_bn=0):
+    M, K = x.shape
+    N = W.shape[0]
+    tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
+    out = torch.full((M, N), float("nan"), dtype=tdt, device="cuda") if want_out else None
+    of = torch.full((M, N), float("nan"), dtype=torch.float32, device="cuda") if want_f32 else None
+    pre = torch.full((M, N), float("nan"), dtype=tdt, device="cuda") if want_pre else None
+    L.check(L.lib().fervit_linear_forward(dtype, x.data_ptr(), W.data_ptr(), ptr(bias), ptr(residual), M, N, K, act,
+                                          ptr(out), ptr(of), ptr(pre), force_bn, st()))
+    torch.cuda.synchronize()
+    return out, of, pre
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (200, 192, 100), (608, 1536, 512), (1000, 64, 2048)])
+def test_gemm_fp32_simt(lib, M, N, K):
+    L = lib
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    out, of, pre = run_linear(L, L.F32, x, W, b, r, L.ACT_GELU, True, True, True)
+    u = (x.double() @ W.double().t() + b.double())
+    ref = gelu(u) + r.double()
+    e1, e2 = relerr(of, ref), relerr(pre, u)
+    record("gemm_fp32_simt", M=M, N=N, K=K, err_out=e1, err_pre=e2)
+    assert e1 < 1e-5 and e2 < 1e-5 and torch.equal(out, of)
+
+
+TC_SHAPES = [
+    # M, N, K, force_bn
+    (128, 64, 64, 64), (128, 128, 64, 128), (128, 256, 64, 256),      # one tile, one k-block
+    (128, 128, 256, 128),                                              # k loop / descriptor K-advance
+    (384, 256, 512, 0),                                                # several tiles
+    (300, 192, 136, 0),                                                # ragged M (TMA zero fill), N % BN != 0, K tail
+    (4864, 2304, 768, 0), (4864, 768, 768, 0), (4864, 3072, 768, 0), (4864, 768, 3072, 0),   # ViT-B @ B=256
+    (4864, 64, 768, 0), (4864, 768, 64, 0),                            # adapter
+    (4608, 768, 512, 0),                                               # token projection
+    (19 * 7, 768, 768, 0),                                             # tiny batch
+]
+
+
+@pytest.mark.parametrize("M,N,K,bn", TC_SHAPES)
+def test_gemm_bf16_tcgen05(lib, M, N, K, bn):
+    L = lib
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    # plain
+    out, of, _ = run_linear(L, L.BF16, x, W, None, None, L.ACT_NONE, True, True, False, bn)
+    ref = x.float() @ W.float().t()
+    e_plain = relerr(of, ref)
+    # full epilogue
+    out2, of2, pre2 = run_linear(L, L.BF16, x, W, b, r, L.ACT_GELU, True, True, True, bn)
+    u = ref + b
+    ref2 = gelu(u) + r
+    e_full, e_pre, e_bf = relerr(of2, ref2), relerr(pre2.float(), u), relerr(out2.float(), ref2)
+    record("gemm_bf16_tcgen05", M=M, N=N, K=K, bn=bn, err_plain=e_plain, err_full=e_full, err_pre=e_pre, err_bf16=e_bf)
+    assert not torch.isnan(of).any() and not torch.isnan(of2).any()
+    assert e_plain < 2e-5, "fp32-accumulated output must match an fp32 matmul of the same bf16 inputs"
+    assert e_full < 2e-5 and e_pre < 4e-3 and e_bf < 4e-3
+    assert relerr(out.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(256, 64, 64), (4864, 64, 768), (4864, 768, 64), (608, 1536, 512),
+                                   (1000, 128, 200), (4608, 768, 512), (4864, 768, 3072)])
+def test_linear_wgrad(lib, dtype_name, M, N, K):
+    """dW[N,K] = alpha * dY^T X over M token rows: MN-major tcgen05 operands (bf16) / strided fp32 GEMM, split-K."""
+    L = lib
+    dtype = L.F32 if dtype_name == "fp32" else L.BF16
+    tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + 13 * N + K)
+    dY = torch.randn(M, N, device="cuda", generator=g).to(tdt)
+    X = torch.randn(M, K, device="cuda", generator=g).to(tdt)
+    dW = torch.full((N, K), float("nan"), device="cuda")
+    scratch = torch.empty(int(L.lib().fervit_linear_wgrad_scratch_floats(M, N, K)), device="cuda")
+    L.check(L.lib().fervit_linear_wgrad(dtype, dY.data_ptr(), X.data_ptr(), M, N, K, 0.5, dW.data_ptr(),
+                                        scratch.data_ptr(), st()))
+    torch.cuda.synchronize()
+    ref = 0.5 * (dY.double().t() @ X.double())
+    e = relerr(dW, ref)
+    record("linear_wgrad", dtype=dtype_name, M=M, N=N, K=K, err=e)
+    assert e < 2e-5
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("rows,E", [(37, 64), (608, 512), (4864, 768), (130, 192)])
+def test_layernorm(lib, dtype_name, rows, E):
+    L = lib
+    dtype = L.F32 if dtype_name == "fp32" else L.BF16
+    tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(rows + E)
+    x = torch.randn(rows, E, device="cuda", generator=g) * 2 + 0.5
+    gam = 1 + 0.2 * torch.randn(E, device="cuda", generator=g)
+    bet = 0.2 * torch.randn(E, device="cuda", generator=g)
+    dy = torch.randn(rows, E, device="cuda", generator=g).to(tdt)
+    dres = torch.randn(rows, E, device="cuda", generator=g)
+    yf = torch.empty(rows, E, device="cuda")
+    ya = torch.empty(rows, E, device="cuda", dtype=tdt)
+    mean = torch.empty(rows, device="cuda"); rstd = torch.empty(rows, device="cuda")
+    L.check(L.lib().fervit_layernorm_forward(dtype, x.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1e-6, rows, E,
+                                             yf.data_ptr(), ya.data_ptr(), mean.data_ptr(), rstd.data_ptr(), st()))
+    xd = x.double().requires_grad_(True); gd = gam.double().requires_grad_(True); bd = bet.double().requires_grad_(True)
+    mu = xd.mean(-1, keepdim=True); var = ((xd - mu) ** 2).mean(-1, keepdim=True)
+    ref = (xd - mu) / torch.sqrt(var + 1e-6) * gd + bd
+    dxr, dgr, dbr = torch.autograd.grad(ref, [xd, gd, bd], dy.double())
+    dxf = torch.empty(rows, E, device="cuda"); dxa = torch.empty(rows, E, device="cuda", dtype=tdt)
+    dgam = torch.empty(E, device="cuda"); dbet = torch.empty(E, device="cuda")
+    scratch = torch.empty(int(L.lib().fervit_layernorm_scratch_floats(rows, E)), device="cuda")
+    L.check(L.lib().fervit_layernorm_backward(dtype, dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                              gam.data_ptr(), dres.data_ptr(), rows, E, dxf.data_ptr(), dxa.data_ptr(),
+                                              scratch.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), st()))
+    torch.cuda.synchronize()
+    errs = dict(y=relerr(yf, ref), y_act=relerr(ya.float(), ref), dx=relerr(dxf, dxr + dres.double()),
+                dgamma=relerr(dgam, dgr), dbeta=relerr(dbet, dbr))
+    record("layernorm", dtype=dtype_name, rows=rows, E=E, **errs)
+    tol_act = 1e-5 if dtype == L.F32 else 4e-3
+    assert errs["y"] < 1e-5 and errs["y_act"] < tol_act and errs["dx"] < 1e-5
+    assert errs["dgamma"] < 1e-5 and errs["dbeta"] < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def attn_ref(qkv, B, S, H, hd, mask=None):
+    E = H * hd
+    q, k, v = qkv.reshape(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q @ k.transpose(-1, -2)) / math.sqrt(hd), dim=-1)
+    if mask is not None:
+        p = p * mask
+    return (p @ v).permute(0, 2, 1, 3).reshape(B * S, E)
+
+
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,S,H,hd,pdrop", [(5, 19, 2, 32, 0.0), (33, 19, 12, 64, 0.0), (3, 37, 6, 64, 0.0),
+                                            (2, 197, 8, 64, 0.0), (2, 197, 8, 48, 0.0), (4, 19, 8, 64, 0.1),
+                                            (2, 5, 2, 32, 0.1)])
+def test_attention(lib, dtype_name, B, S, H, hd, pdrop):
+    L = lib
+    dtype = L.F32 if dtype_name == "fp32" else L.BF16
+    tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(B + S + H + hd)
+    qkv = torch.randn(B * S, 3 * E, device="cuda", generator=g).to(tdt)
+    dout = torch.randn(B * S, E, device="cuda", generator=g).to(tdt)
+    out = torch.empty(B * S, E, device="cuda", dtype=tdt)
+    lse = torch.empty(B * H * S, device="cuda")
+    dqkv = torch.empty(B * S, 3 * E, device="cuda", dtype=tdt)
+    seed, site = 1234, 8
+    L.check(L.lib().fervit_attention_forward(dtype, qkv.data_ptr(), B, S, H, hd, pdrop, seed, site, out.data_ptr(),
+                                             lse.data_ptr(), st()))
+    L.check(L.lib().fervit_attention_backward(dtype, qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                              B, S, H, hd, pdrop, seed, site, dqkv.data_ptr(), st()))
+    mask = None
+    if pdrop > 0:
+        mask = torch.empty(B * H * S * S, device="cuda")
+        L.check(L.lib().fervit_dropout_mask(mask.data_ptr(), mask.numel(), pdrop, seed, site, st()))
+        mask = mask.reshape(B, H, S, S).double()
+        keep = (mask > 0).double().mean().item()
+        assert abs(keep - (1 - pdrop)) < 0.05 and torch.all((mask == 0) | ((mask - 1 / (1 - pdrop)).abs() < 1e-6))
+    torch.cuda.synchronize()
+    qd = qkv.double().requires_grad_(True)
+    ref = attn_ref(qd, B, S, H, hd, mask)
+    dref, = torch.autograd.grad(ref, qd, dout.double())
+    e_o, e_d = relerr(out.float(), ref), relerr(dqkv.float(), dref)
+    record("attention", dtype=dtype_name, B=B, S=S, H=H, hd=hd, p=pdrop, err_out=e_o, err_dqkv=e_d)
+    tol = 2e-5 if dtype == L.F32 else 6e-3
+    assert e_o < tol and e_d < tol
+
+
+# ------------------------------------------------------------------------------------------------ loss
+@pytest.mark.parametrize("B", [1, 6, 256, 4096])
+@pytest.mark.parametrize("weighted,eps", [(False, 0.0), (True, 0.0), (False, 0.1), (True, 0.1)])
+def test_cross_entropy(lib, B, weighted, eps):
+    import fer_vit_b200 as fv
+    g = torch.Generator(device="cuda").manual_seed(B)
+    z = (3 * torch.randn(B, 7, device="cuda", generator=g)).requires_grad_(True)
+    y = torch.randint(0, 7, (B,), device="cuda", generator=g)
+    w = (torch.rand(7, device="cuda", generator=g) + 0.5) if weighted else None
+    loss = fv.cross_entropy(z, y, w, eps)
+    gz, = torch.autograd.grad(loss, z)
+    zr = z.detach().double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(zr, y, weight=w.double() if weighted else None, label_smoothing=eps)
+    gr, = torch.autograd.grad(ref, zr)
+    e_l, e_g = abs(loss.item() - ref.item()) / abs(ref.item()), relerr(gz, gr)
+    record("cross_entropy", B=B, weighted=weighted, eps=eps, err_loss=e_l, err_grad=e_g)
+    assert e_l < 1e-5 and e_g < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ pre-modules
+@pytest.mark.parametrize("flags", [(1, 0, 0, 0), (0, 1, 0, 0), (0, 1, 1, 0), (0, 0, 0, 1), (1, 1, 1, 1), (1, 1, 0, 1)])
+@pytest.mark.parametrize("B,D", [(3, 64), (37, 512)])
+def test_premodules(lib, flags, B, D):
+    import fer_vit_b200 as fv
+    from oracle import reference_math as R
+    use_spe, use_lwn, use_res, use_leam = flags
+    torch.manual_seed(sum(flags) + B)
+    Ln = 18
+    x = (torch.randn(B, Ln, D) * 0.8 + 0.2).cuda().requires_grad_(True)
+    mods = {}
+    if use_spe:
+        mods["spe"] = fv.SemanticPE(D, Ln).cuda()
+    if use_lwn:
+        mods["lwn"] = fv.LayerWiseNorm(Ln, D, use_residual=bool(use_res)).cuda()
+        with torch.no_grad():
+            for n in mods["lwn"].norms:
+                n.weight.add_(0.2 * torch.randn_like(n.weight)); n.bias.add_(0.2 * torch.randn_like(n.bias))
+            if use_res:
+                mods["lwn"].gate.add_(4.5 + torch.randn_like(mods["lwn"].gate))
+    if use_leam:
+        mods["leam"] = fv.LEAM(Ln).cuda()
+    h = x
+    for k in ("spe", "lwn", "leam"):
+        if k in mods:
+            h = mods[k](h)
+    dy = torch.randn_like(h)
+    params = [p for m in mods.values() for p in m.parameters()]
+    names = [f"{k}.{n}" for k, m in mods.items() for n, _ in m.named_parameters()]
+    grads = torch.autograd.grad(h, [x] + params, dy)
+    sd = {}
+    for k, m in mods.items():
+        for n, v in m.state_dict().items():
+            t = v.detach().cpu()
+            sd[f"{k}.{n}"] = t.double().requires_grad_(True) if t.is_floating_point() else t
+    xr = x.detach().cpu().double().requires_grad_(True)
+    ref = R.pre_modules(xr, sd, bool(use_spe), bool(use_lwn), bool(use_res), bool(use_leam))
+    rg = torch.autograd.grad(ref, [xr] + [sd[n] for n in names], dy.cpu().double())
+    errs = {"y": relerr(h, ref), "dx": relerr(grads[0], rg[0])}
+    for n, a, b in zip(names, grads[1:], rg[1:]):
+        errs["d" + n] = relerr(a, b)
+    record("premodules", flags=list(flags), B=B, D=D, worst=max(errs.values()))
+    assert max(errs.values()) < 2e-5, errs
