@@ -56,6 +56,8 @@ SIGNATURES = {
     "fervit_abi_version": (_i, []),
     "fervit_last_error": (C.c_char_p, []),
     "fervit_launch_count": (_u64, []),
+    "fervit_profile_enable": (_i, [_i]),
+    "fervit_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_ll)]),
     "fervit_plan_create": (_i, [C.POINTER(Config), C.POINTER(_p)]),
     "fervit_plan_destroy": (None, [_p]),
     "fervit_plan_num_slots": (_i, [_p]),

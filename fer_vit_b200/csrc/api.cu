@@ -14,6 +14,16 @@ FV_API int fervit_abi_version(void) { return FERVIT_ABI_VERSION; }
 FV_API const char* fervit_last_error(void) { return get_error(); }
 FV_API unsigned long long fervit_launch_count(void) { return g_launch_count; }
 
+FV_API int fervit_profile_enable(int on) {
+  prof_enable(on != 0);
+  return 0;
+}
+FV_API int fervit_profile_read(int kernel_class, double* ms, double* work, long long* launches) {
+  FV_CHECK(ms && work && launches, "profile_read: null argument");
+  FV_CHECK(prof_read(kernel_class, ms, work, launches) == 0, "profile_read: CUDA event query failed");
+  return 0;
+}
+
 FV_API int fervit_cross_entropy(const float* logits, const long long* labels, const float* weight,
                                 float label_smoothing, int B, int C, const float* den_in, float grad_scale,
                                 float* loss, float* dlogits, float* den_out, void* stream) {

@@ -107,13 +107,14 @@ __global__ void attn_bwd_kernel(const AT* __restrict__ qkv, const AT* __restrict
   const int i = threadIdx.x % SP;
   const int bh = blockIdx.x * G + g;
   const bool valid = bh < B * H;
-  const size_t per_group = (size_t)4 * S * LD + 2 * S;
+  const int SA = (S + 3) & ~3;  // keep every group 16-byte aligned
+  const size_t per_group = (size_t)4 * S * LD + 2 * SA;
   float* Qs = smem + (size_t)g * per_group;
   float* Ks = Qs + S * LD;
   float* Vs = Ks + S * LD;
   float* dOs = Vs + S * LD;
   float* Ls = dOs + S * LD;
-  float* Ds = Ls + S;
+  float* Ds = Ls + SA;
   const int b = valid ? bh / H : 0, h = valid ? bh % H : 0;
   const AT* base = qkv + (size_t)b * S * 3 * E + h * HD;
   const AT* obase = out + (size_t)b * S * E + h * HD;
@@ -242,6 +243,8 @@ static int attention_fwd_t(const AT* qkv, AT* out, float* lse, int B, int S, int
     smem_set = smem;
   }
   const float scale = 1.0f / sqrtf((float)HD);
+  // algorithmic bytes: read Q,K,V once, write O once (+ LSE)
+  ProfScope prof(1, (double)B * S * H * HD * 4.0 * sizeof(AT) + (double)B * H * S * 4.0, stream);
   kern<<<ceil_div(B * H, G), SP * G, smem, stream>>>(qkv, out, lse, B, S, H, SP, G, scale, drop);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
@@ -253,7 +256,7 @@ static int attention_bwd_t(const AT* qkv, const AT* out, const AT* dout, const f
                            int H, Dropout drop, cudaStream_t stream) {
   int SP, G;
   attn::geometry(S, SP, G);
-  const size_t smem = (size_t)G * ((size_t)4 * S * attn::Pad<HD>::LD + 2 * S) * sizeof(float);
+  const size_t smem = (size_t)G * ((size_t)4 * S * attn::Pad<HD>::LD + 2 * ((S + 3) & ~3)) * sizeof(float);
   FV_CHECK(smem <= 227 * 1024, "attention_bwd: sequence length %d does not fit in shared memory", S);
   FV_CHECK(SP * G <= 1024, "attention_bwd: sequence length %d too long for one CTA", S);
   auto kern = attn::attn_bwd_kernel<AT, HD>;
@@ -263,6 +266,8 @@ static int attention_bwd_t(const AT* qkv, const AT* out, const AT* dout, const f
     smem_set = smem;
   }
   const float scale = 1.0f / sqrtf((float)HD);
+  // algorithmic bytes: read Q,K,V,O,dO once, write dQ,dK,dV once (+ LSE)
+  ProfScope prof(1, (double)B * S * H * HD * 8.0 * sizeof(AT) + (double)B * H * S * 4.0, stream);
   kern<<<ceil_div(B * H, G), SP * G, smem, stream>>>(qkv, out, dout, lse, dqkv, B, S, H, SP, G, scale, drop);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();

@@ -49,6 +49,19 @@ extern unsigned long long g_launch_count;
 
 int num_sms();
 
+// per-kernel-class event timing (runtime.cu); classes: 0 tcgen05 GEMM (flops), 1 attention (bytes),
+// 2 LayerNorm (bytes), 3 fp32 GEMM (flops)
+bool prof_enabled();
+int prof_open(int cls, double work, cudaStream_t st);
+void prof_close(int id, cudaStream_t st);
+void prof_enable(bool on);
+int prof_read(int cls, double* ms, double* work, long long* count);
+struct ProfScope {
+  int id; cudaStream_t st;
+  ProfScope(int cls, double work, cudaStream_t s) : id(-1), st(s) { if (prof_enabled()) id = prof_open(cls, work, s); }
+  ~ProfScope() { if (id >= 0) prof_close(id, st); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Activation ids used by GEMM epilogues and the oracle alike.
 // ---------------------------------------------------------------------------------------------

@@ -112,6 +112,7 @@ int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, 
                  epi.act == 0 && epi.act_bwd == 0 && epi.out_pre == nullptr && epi.remap_L == 0 && epi.ldo == N,
              "gemm_f32_simt: split-K supports only a plain fp32 partial output");
   dim3 grid(ceil_div(N, simt::TN), ceil_div(M, simt::TM), splits);
+  ProfScope prof(3, 2.0 * M * (double)N * K, stream);
   simt::gemm_simt_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbn, sbk, M, N, K, k_per_split, epi);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();

@@ -267,9 +267,18 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels
     }
     lsum += li;
     if (dlogits) {
+      // sum_c dlogits[i,c] == 0 exactly (softmax sums to 1), so the target class takes minus the sum of the
+      // others: avoids the cancellation in softmax[y] - 1 when the sample is already classified with p ~ 1
+      float others = 0.f;
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c)
-        if (c < C) dlogits[(size_t)i * C + c] = grad_scale * (expf(zl[c] - lse) * tsum - t[c]) / den;
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C && c != y) {
+          const float d = grad_scale * (expf(zl[c] - lse) * tsum - t[c]) / den;
+          dlogits[(size_t)i * C + c] = d;
+          others += d;
+        }
+      }
+      dlogits[(size_t)i * C + y] = -others;
     }
   }
   lsum = warp_sum(lsum);

@@ -166,6 +166,9 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
                   AT* out_at, float* mean, float* rstd, cudaStream_t stream) {
   FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (rows <= 0) return 0;
+  // algorithmic bytes: read x fp32, write each requested output, 8 B of statistics per row
+  ProfScope prof(2, (double)rows * E * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0,
+                 stream);
   ln::ln_fwd_kernel<AT><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(x, gamma, beta, eps, rows, E,
                                                                                out_f32, out_at, mean, rstd);
   FV_COUNT_LAUNCH();
@@ -186,6 +189,9 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
                   cudaStream_t stream) {
   FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (rows <= 0) return 0;
+  // algorithmic bytes: read dy and x (and dres), write each requested output, 8 B of statistics per row
+  ProfScope prof(2, (double)rows * E * ((double)sizeof(DT) + 4.0 + (dres ? 4.0 : 0.0) + (dx_f32 ? 4.0 : 0.0) +
+                                        (dx_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0, stream);
   if (partial) {
     const int grid = layernorm_bwd_grid(rows);
     ln::ln_bwd_kernel<DT, AT, true><<<grid, ln::WARPS * 32, 0, stream>>>(dy, x, mean, rstd, gamma, dres, rows, E,

@@ -1,6 +1,7 @@
 // Library-wide runtime state: last-error string, SM count, launch counter.
 #include "common.cuh"
 #include <stdarg.h>
+#include <vector>
 
 namespace fervit {
 
@@ -23,6 +24,45 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
   return sms;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg).
+// Off by default; never enabled inside a timed region or a graph capture.
+// ---------------------------------------------------------------------------------------------
+struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+bool prof_enabled() { return g_prof_on; }
+int prof_open(int cls, double work, cudaStream_t st) {
+  ProfRec r;
+  r.cls = cls; r.work = work;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+  return (int)g_prof.size() - 1;
+}
+void prof_close(int id, cudaStream_t st) {
+  if (id >= 0 && id < (int)g_prof.size()) cudaEventRecord(g_prof[id].b, st);
+}
+void prof_enable(bool on) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = on;
+}
+int prof_read(int cls, double* ms, double* work, long long* count) {
+  double tm = 0, w = 0; long long n = 0;
+  for (auto& r : g_prof) {
+    if (r.cls != cls) continue;
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return 1;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return 1;
+    tm += t; w += r.work; ++n;
+  }
+  *ms = tm; *work = w; *count = n;
+  return 0;
 }
 
 }  // namespace fervit

