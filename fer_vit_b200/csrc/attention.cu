@@ -7,6 +7,7 @@
 // qkv layout: [B*S, 3E], columns [Q | K | V], head h at columns h*HD .. (timm qkv / torch in_proj packing).
 #include "common.cuh"
 #include "kernels.h"
+#include <type_traits>
 
 namespace fervit {
 
@@ -276,6 +277,10 @@ static int attention_bwd_t(const AT* qkv, const AT* out, const AT* dout, const f
 
 template <typename AT>
 int attention_fwd(const AT* qkv, AT* out, float* lse, int B, int S, int H, int HD, Dropout drop, cudaStream_t stream) {
+  if constexpr (std::is_same<AT, bf16>::value) {
+    // S <= 32: warp-per-head tensor-core kernel (attention_tc.cu); longer sequences use the kernel below
+    if (attention_tc_supported(S, HD)) return attention_tc_fwd(qkv, out, lse, B, S, H, HD, drop, stream);
+  }
   if (HD == 64) return attention_fwd_t<AT, 64>(qkv, out, lse, B, S, H, drop, stream);
   if (HD == 48) return attention_fwd_t<AT, 48>(qkv, out, lse, B, S, H, drop, stream);
   if (HD == 32) return attention_fwd_t<AT, 32>(qkv, out, lse, B, S, H, drop, stream);
@@ -284,6 +289,9 @@ int attention_fwd(const AT* qkv, AT* out, float* lse, int B, int S, int H, int H
 template <typename AT>
 int attention_bwd(const AT* qkv, const AT* out, const AT* dout, const float* lse, AT* dqkv, int B, int S, int H,
                   int HD, Dropout drop, cudaStream_t stream) {
+  if constexpr (std::is_same<AT, bf16>::value) {
+    if (attention_tc_supported(S, HD)) return attention_tc_bwd(qkv, out, dout, lse, dqkv, B, S, H, HD, drop, stream);
+  }
   if (HD == 64) return attention_bwd_t<AT, 64>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);
   if (HD == 48) return attention_bwd_t<AT, 48>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);
   if (HD == 32) return attention_bwd_t<AT, 32>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);

@@ -1,14 +1,43 @@
 // The one GEMM epilogue used by every dense contraction on the path (see common.cuh: Epilogue).
+//
+// It is specialised at COMPILE time on its "kind": a kernel instantiation carries only the code its epilogue needs
+// (exact-erf GELU and its derivative, the dropout hash and the token-row remap are each ~40-100 instructions; with
+// all of them inlined behind runtime flags the persistent tcgen05 kernel outgrew the instruction cache and its
+// epilogue warps ran ~2x slower than the MMAs they were supposed to hide behind — measured).
 #pragma once
 #include "common.cuh"
 
 namespace fervit {
 
+enum EpiKind {
+  EPK_PLAIN = 0,     // bias / alpha / residual / outputs only
+  EPK_GELU,          // + forward GELU (pre-activation optionally stored)
+  EPK_RELU,          // + forward ReLU
+  EPK_GELU_BWD,      // accumulator times GELU'(aux)
+  EPK_RELU_BWD,      // accumulator times ReLU'(aux)
+  EPK_REMAP,         // token rows skip the cls slot, + position rows (input projection)
+  EPK_GENERIC,       // everything behind runtime flags (dropout, unusual combinations)
+  EPK_COUNT
+};
+
+// host: the cheapest kind that implements `e`
+static inline int epilogue_kind(const Epilogue& e) {
+  if (e.drop.threshold) return EPK_GENERIC;
+  if (e.remap_L > 0) return (e.act == ACT_NONE && e.act_bwd == ACT_NONE) ? EPK_REMAP : EPK_GENERIC;
+  if (e.act != ACT_NONE && e.act_bwd != ACT_NONE) return EPK_GENERIC;
+  if (e.act == ACT_GELU) return EPK_GELU;
+  if (e.act == ACT_RELU) return EPK_RELU;
+  if (e.act_bwd == ACT_GELU) return EPK_GELU_BWD;
+  if (e.act_bwd == ACT_RELU) return EPK_RELU_BWD;
+  return EPK_PLAIN;
+}
+
 // Apply the epilogue to NV consecutive columns [col, col+NV) of logical row `row`.
 // Caller guarantees row < M and col + NV <= N, NV % 4 == 0 and col % 4 == 0.
-template <typename AT, int NV>
-__device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, int row, int col,
-                                               int N, float (&v)[NV]) {
+template <typename AT, int NV, int KIND>
+__device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, int row, int col, int N,
+                                               float (&v)[NV]) {
+  constexpr bool GEN = (KIND == EPK_GENERIC);
   if (e.bias) {
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
@@ -16,55 +45,65 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
       v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
   }
-  if (e.act_bwd != ACT_NONE) {
+  if (GEN ? (e.act_bwd != ACT_NONE) : (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD)) {
     const AT* aux = reinterpret_cast<const AT*>(e.aux) + (size_t)row * N + col;
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
       const float4 a = load4<AT>(aux + i);
-      v[i] *= act_bwd(e.act_bwd, a.x);
-      v[i + 1] *= act_bwd(e.act_bwd, a.y);
-      v[i + 2] *= act_bwd(e.act_bwd, a.z);
-      v[i + 3] *= act_bwd(e.act_bwd, a.w);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float d;
+        if (GEN) d = act_bwd(e.act_bwd, av[t]);
+        else if (KIND == EPK_GELU_BWD) d = gelu_bwd(av[t]);
+        else d = av[t] > 0.0f ? 1.0f : 0.0f;
+        v[i + t] *= d;
+      }
     }
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i) v[i] *= alpha;
-  if (e.out_pre) {
-    AT* p = reinterpret_cast<AT*>(e.out_pre) + (size_t)row * N + col;
+  if (GEN ? (e.act != ACT_NONE) : (KIND == EPK_GELU || KIND == EPK_RELU)) {
+    if (e.out_pre) {
+      AT* p = reinterpret_cast<AT*>(e.out_pre) + (size_t)row * N + col;
 #pragma unroll
-    for (int i = 0; i < NV; i += 4) store4<AT>(p + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      for (int i = 0; i < NV; i += 4) store4<AT>(p + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (GEN) v[i] = act_fwd(e.act, v[i]);
+      else if (KIND == EPK_GELU) v[i] = gelu_fwd(v[i]);
+      else v[i] = fmaxf(v[i], 0.0f);
+    }
   }
-  if (e.act != ACT_NONE) {
+  if (GEN) {
+    if (e.drop.threshold) {
+      const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col;
+      const uint64_t seed = e.drop.eff();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = act_fwd(e.act, v[i]);
-  }
-  if (e.drop.threshold) {
-    const uint64_t base = (uint64_t)row * (uint64_t)N + (uint64_t)col;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      v[i] = drop_keep(e.drop.eff(), e.drop.site, base + i, e.drop.threshold) ? v[i] * e.drop.scale : 0.0f;
+      for (int i = 0; i < NV; ++i)
+        v[i] = drop_keep(seed, e.drop.site, base + i, e.drop.threshold) ? v[i] * e.drop.scale : 0.0f;
+    }
   }
   int orow = row;
-  int prow = 0;
-  if (e.remap_L > 0) {
+  if (GEN ? (e.remap_L > 0) : (KIND == EPK_REMAP)) {
     const int b = row / e.remap_L;
     const int l = row - b * e.remap_L;
     orow = b * (e.remap_L + 1) + 1 + l;
-    prow = 1 + l;
+    if (e.pos) {
+      const float* pp = e.pos + (size_t)(1 + l) * N + col;
+#pragma unroll
+      for (int i = 0; i < NV; i += 4) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(pp + i));
+        v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+      }
+    }
   }
   const size_t ooff = (size_t)orow * e.ldo + col;
   if (e.residual) {
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
       const float4 r = *reinterpret_cast<const float4*>(e.residual + ooff + i);
-      v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-    }
-  }
-  if (e.pos) {
-    const float* pp = e.pos + (size_t)prow * N + col;
-#pragma unroll
-    for (int i = 0; i < NV; i += 4) {
-      const float4 r = __ldg(reinterpret_cast<const float4*>(pp + i));
       v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
     }
   }

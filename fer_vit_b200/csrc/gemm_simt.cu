@@ -93,7 +93,7 @@ gemm_simt_kernel(const float* __restrict__ A, long long sam, long long sak, cons
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
-    if (row < M) epilogue_apply<float, 4>(epi, alpha, row, col, N, acc[i]);
+    if (row < M) epilogue_apply<float, 4, EPK_GENERIC>(epi, alpha, row, col, N, acc[i]);
   }
 }
 

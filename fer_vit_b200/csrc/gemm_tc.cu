@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "epilogue.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace fervit {
 
@@ -35,7 +36,10 @@ struct Cfg {
   static constexpr int STAGES = (BN == 256) ? 4 : ((BN == 128) ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // 128 / 256 / 512: powers of two
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment
+  // per-epilogue-warp transposition buffer: 32 rows x 16 columns fp32, row stride 20 words (conflict-free float4)
+  static constexpr int EPI_LD = 20;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_BYTES + 1024;  // +1024: manual alignment
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -64,9 +68,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (the launch then fails loudly) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a protocol bug traps (the launch then fails loudly) instead of hanging the GPU. The slow path is
+// kept out of line so the hot loops stay small.
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000ll) {
@@ -74,6 +78,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
                                             int c1) {
@@ -138,10 +147,11 @@ struct Params {
   int M, N, K;        // logical problem
   int splits;         // split-K factor (1 = none); >1 writes fp32 partials to epi.out_f32 + split*M*N
   int kb_per_split;   // k-blocks per split
+  int debug;          // bit mask for timing experiments (results are garbage): 1 skip TMA loads, 2 skip MMAs, 4 skip the epilogue, 8 epilogue = TMEM loads only
   Epilogue epi;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const Params p) {
@@ -156,6 +166,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* tmem_full = bars + 2 * C::STAGES;
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+  float* epi_stage = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +216,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (p.debug & 1) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * C::A_BYTES;
           uint8_t* sb = smem_b + stage * C::B_BYTES;
@@ -245,6 +261,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          if (p.debug & 2) {
+            mbar_arrive(&empty_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
@@ -260,7 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[buf]);  // accumulator complete
+        if (p.debug & 2) mbar_arrive(&tmem_full[buf]);
+        else umma_commit(&tmem_full[buf]);  // accumulator complete
       }
     }
   } else if (warp >= 4) {
@@ -280,17 +302,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t acc_phase = (it >> 1) & 1;
       Epilogue e = p.epi;
       if (p.splits > 1) e.out_f32 = p.epi.out_f32 + (size_t)split * (size_t)p.M * (size_t)p.N;
+      if (p.debug & 16) { e.out = nullptr; e.out_f32 = nullptr; e.out_pre = nullptr; }
       mbar_wait(&tmem_full[buf], acc_phase);
       tcgen05_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
+      const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP);
+      float* stg = epi_stage + (warp - 4) * (32 * C::EPI_LD);
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 16) {
         const int col = n_blk * BN + half * COLS_PER_WARP + c;
         if (col >= p.N) break;  // warp-uniform
+        if (p.debug & 4) break;
         float v[16];
         tmem_ld16(taddr0 + (uint32_t)c, v);
-        if (row < p.M) epilogue_apply<bf16, 16>(e, alpha, row, col, p.N, v);
+        if (p.debug & 8) continue;
+        // TMEM hands each lane one ROW of the tile; global memory wants lanes side by side along a row.
+        // Transpose the 32x16 chunk through shared memory so every epilogue load/store below is coalesced.
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(stg + lane * C::EPI_LD + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr) {
+          const int r = itr * 8 + (lane >> 2), c4 = (lane & 3) * 4;
+          const float4 w = *reinterpret_cast<const float4*>(stg + r * C::EPI_LD + c4);
+          float w4[4] = {w.x, w.y, w.z, w.w};
+          if (p.debug & 32) { if (w4[0] == 1.2345e30f) e.out_f32[0] = w4[1]; continue; }
+          if (row0 + r < p.M) epilogue_apply<bf16, 4, KIND>(e, alpha, row0 + r, col + c4, p.N, w4);
+        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -347,7 +387,7 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int KIND>
 static int launch(const bf16* A, int lda, const bf16* B, int ldb, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN>;
   CUtensorMap ta, tb;
@@ -357,7 +397,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, const Params& 
   else      FV_TRY(make_tmap(&tb, B, (uint64_t)p.K, (uint64_t)p.N, (uint64_t)ldb, BN));
   static bool attr_set = false;
   if (!attr_set) {
-    FV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::SMEM_BYTES));
     attr_set = true;
   }
@@ -365,25 +405,27 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, const Params& 
   const int units = m_blocks * n_blocks * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
   ProfScope prof(0, 2.0 * p.M * (double)p.N * p.K, stream);
-  gemm_tc_kernel<BN, A_MN, B_MN><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, A_MN, B_MN, KIND><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
 }
 
-// Pick the N tile: fewest (waves x per-tile cost); per-tile cost ~ BN * (k-blocks + fixed overhead).
+// Pick the N tile. Measured on B200 (tools/gemm_bench.py, FERVIT_GEMM_DEBUG=5): a cta_group::1 M=128 MMA takes the
+// same ~128 cycles for N = 128 and N = 256 (1660 vs 870 TFLOP/s with loads and epilogue off), so the per-tile cost is
+// ~ (k-blocks * 512 cycles + an epilogue term proportional to BN) whatever BN is: use the widest tile that is not
+// mostly padding, and fall back to a narrower one only when it needs fewer waves.
 static int choose_bn(int M, int N, int kblocks, int splits) {
   const int cands[3] = {256, 128, 64};
   long long best_cost = -1;
-  int best = 128;
+  int best = 256;
   const int sms = num_sms();
   for (int i = 0; i < 3; ++i) {
     const int bn = cands[i];
     if (bn > 64 && N <= bn / 2) continue;  // mostly padding
     const long long tiles = (long long)ceil_div(M, BM) * ceil_div(N, bn) * splits;
     const long long waves = ceil_div_ll(tiles, sms);
-    // small-N tiles run the tensor pipe less efficiently per column (A re-read per tile): mild penalty
-    const long long cost = waves * ((long long)bn * (kblocks + 3) + (bn == 64 ? 16 * kblocks : (bn == 128 ? 4 * kblocks : 0)));
+    const long long cost = waves * ((long long)kblocks * 512 + 6 * bn + 600);
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
   }
   return best;
@@ -406,21 +448,35 @@ int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool
   p.kb_per_split = ceil_div(total_kb, splits);
   p.splits = ceil_div(total_kb, p.kb_per_split);
   p.epi = epi;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FERVIT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   if (p.splits > 1)
     FV_CHECK(epi.out_f32 != nullptr && epi.out == nullptr && epi.bias == nullptr && epi.residual == nullptr &&
                  epi.act == 0 && epi.act_bwd == 0 && epi.out_pre == nullptr && epi.remap_L == 0 && epi.ldo == N,
              "gemm_bf16_tc: split-K supports only a plain fp32 partial output");
   int bn = force_bn > 0 ? force_bn : tc::choose_bn(M, N, p.kb_per_split, p.splits);
-#define FV_TC_DISPATCH(BN_)                                                                               \
-  do {                                                                                                    \
-    if (!a_mn && !b_mn) return tc::launch<BN_, false, false>(A, lda, B, ldb, p, stream);                  \
-    if (a_mn && b_mn) return tc::launch<BN_, true, true>(A, lda, B, ldb, p, stream);                      \
-    if (a_mn && !b_mn) return tc::launch<BN_, true, false>(A, lda, B, ldb, p, stream);                    \
-    return tc::launch<BN_, false, true>(A, lda, B, ldb, p, stream);                                       \
+  const int kind = epilogue_kind(epi);
+  if (a_mn != b_mn) { set_error("gemm_bf16_tc: mixed operand major-ness is not instantiated"); return 1; }
+#define FV_TC_KIND(BN_, K_) case K_: return tc::launch<BN_, false, false, K_>(A, lda, B, ldb, p, stream);
+#define FV_TC_DISPATCH(BN_)                                                                  \
+  do {                                                                                       \
+    if (a_mn) {                                                                              \
+      if (kind != EPK_PLAIN) { set_error("gemm_bf16_tc: wgrad supports a plain epilogue only"); return 1; } \
+      return tc::launch<BN_, true, true, EPK_PLAIN>(A, lda, B, ldb, p, stream);              \
+    }                                                                                        \
+    switch (kind) {                                                                          \
+      FV_TC_KIND(BN_, EPK_PLAIN) FV_TC_KIND(BN_, EPK_GELU) FV_TC_KIND(BN_, EPK_RELU)         \
+      FV_TC_KIND(BN_, EPK_GELU_BWD) FV_TC_KIND(BN_, EPK_RELU_BWD) FV_TC_KIND(BN_, EPK_REMAP)  \
+      default: return tc::launch<BN_, false, false, EPK_GENERIC>(A, lda, B, ldb, p, stream);  \
+    }                                                                                        \
   } while (0)
   if (bn == 256) FV_TC_DISPATCH(256);
   if (bn == 128) FV_TC_DISPATCH(128);
   if (bn == 64) FV_TC_DISPATCH(64);
+#undef FV_TC_KIND
 #undef FV_TC_DISPATCH
   FV_CHECK(false, "gemm_bf16_tc: unsupported BN %d", bn);
 }
