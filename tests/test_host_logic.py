@@ -1,0 +1,189 @@
+"""CPU: host-side logic of the drop-in layer — checkpoint/key compatibility with the reference, plan descriptions,
+failure behaviour without CUDA, and the data-parallel gradient bucketing on gloo with world_size 2."""
+import copy
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.util import FIXTURES, build_model, load_golden
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_state_dict_is_interchangeable_with_the_reference(name):
+    """Same keys, shapes and dtypes as the checkpoint the UNMODIFIED reference class wrote (golden fixture)."""
+    g = load_golden(name)
+    model = build_model(name, "fp32")
+    sd = model.state_dict()
+    assert set(sd) == set(g["sd"])
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(g["sd"][k].shape), k
+        assert v.dtype == g["sd"][k].dtype, k
+    model.load_state_dict(g["sd"], strict=True)
+    # requires_grad pattern = set of tensors the reference produced gradients for
+    trainable = {k for k, p in model.named_parameters() if p.requires_grad}
+    assert trainable == set(g["grad"])
+
+
+def test_parameter_counts_match_the_survey():
+    import fer_vit_b200 as fv
+    assert sum(p.numel() for p in fv.LatentViT().parameters()) == 19_191_815
+    v2 = fv.LatentViTv2(use_lwn=True, use_lwn_residual=True, use_spe=True, use_leam=True)
+    assert sum(p.numel() for p in v2.parameters()) == 19_221_035
+    hy = fv.create_hybrid_latent_vit(model_size="base", use_pretrained=False, freeze_transformer=True,
+                                     use_adapter=True, adapter_dim=64)
+    assert sum(p.numel() for p in hy.parameters() if p.requires_grad) == 1_605_907
+    assert sum(p.numel() for p in hy.transformer.parameters()) == 85_054_464
+    assert hy.pos_embed.shape == (1, 19, 768) and hy.embed_dim == 768 and hy.use_adapter
+
+
+def test_hybrid_api_surface_used_by_the_reference_callers():
+    """train_hybrid_latent_vit.py:63-117 and evaluate_model.py:231-296 touch these attributes."""
+    import fer_vit_b200 as fv
+    m = fv.create_hybrid_latent_vit(model_size="tiny", use_pretrained=False, freeze_stages=6, use_adapter=False)
+    assert len(m.transformer) == 12 and hasattr(m.transformer[0], "attn")
+    assert not any(p.requires_grad for p in m.transformer[5].parameters())
+    assert all(p.requires_grad for p in m.transformer[6].parameters())
+    m.unfreeze_all()
+    assert all(p.requires_grad for p in m.parameters())
+    for attr in ("input_proj", "cls_token", "pos_embed", "head", "latent_dim", "seq_len", "num_classes",
+                 "pretrained_model_name"):
+        assert hasattr(m, attr)
+    # the blocks container is callable on CPU tensors (compatibility surface of evaluate_model.py:255)
+    out = m.transformer(torch.randn(2, 19, 192))
+    assert out.shape == (2, 19, 192)
+    assert set(fv.RECOMMENDED_STRATEGIES) == {"full_finetune", "partial_freeze", "adapter", "linear_probe"}
+    with pytest.raises(ImportError):
+        fv.create_hybrid_latent_vit(model_size="tiny", use_pretrained=True)   # needs timm + its download
+
+
+def test_position_embedding_interpolation_matches_reference_formula():
+    """cls row kept, 196 patch rows linearly resampled to seq_len rows (hybrid_latent_vit.py:130-152)."""
+    import torch.nn.functional as F
+    import fer_vit_b200 as fv
+    from fer_vit_b200.models_fer_vit.vit_blocks import VisionTransformerShell
+    torch.manual_seed(0)
+    vit = VisionTransformerShell("vit_tiny_patch16_224")
+    m = fv.HybridLatentViT.__new__(fv.HybridLatentViT)
+    torch.nn.Module.__init__(m)
+    m.embed_dim = 192
+    pos = m._init_position_embedding(vit, 18)
+    ref = torch.cat([vit.pos_embed[:, :1], F.interpolate(vit.pos_embed[:, 1:].permute(0, 2, 1), size=18, mode="linear",
+                                                         align_corners=False).permute(0, 2, 1)], dim=1)
+    assert torch.equal(pos.data, ref.data)
+
+
+def test_plan_description_and_precision_switch():
+    from fer_vit_b200 import _lib as L
+    model = build_model("hybrid_adapter", "bf16")
+    cfg = model._plan_config()
+    assert (cfg.norm_first, cfg.act, cfg.adapter_dim, cfg.E, cfg.depth, cfg.H, cfg.F) == (1, L.ACT_GELU, 16, 64, 2, 2, 256)
+    assert abs(cfg.eps_block - 1e-6) < 1e-12 and abs(cfg.head_dropout - 0.1) < 1e-7
+    runner = model.plan_runner()
+    assert runner.bf16 and runner.nstages == 4
+    slots = [s for stage in runner.stage_slots for s in stage]
+    assert len(slots) == len(set(slots))                      # every slot lives in exactly one backward stage
+    model.precision = "fp32"
+    assert not model.plan_runner().bf16
+    lat = build_model("latent_vit", "fp32")._plan_config()
+    assert (lat.norm_first, lat.act) == (0, L.ACT_RELU) and abs(lat.eps_block - 1e-5) < 1e-9
+    img = build_model("image_vit", "fp32")._plan_config()
+    assert (img.input_kind, img.L, img.Din, img.input_dropout) == (1, 4, 768, 1)
+    with pytest.raises(ValueError):
+        model.precision = "fp16"
+
+
+def test_runner_is_not_part_of_model_state():
+    model = build_model("latent_vit_v2", "fp32")
+    model.plan_runner()
+    clone = copy.deepcopy(model)
+    assert clone.__dict__["_runner"] is None
+    assert not any(k.startswith("_") for k in model.state_dict())
+    assert clone.get_config()["model"] == "LatentViTv2" and clone.get_leam_weights().shape == (18,)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    model = build_model("latent_vit", "fp32")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        model(torch.randn(2, 18, 64))
+    import fer_vit_b200 as fv
+    with pytest.raises(RuntimeError, match="no CPU"):
+        fv.cross_entropy(torch.randn(4, 7, requires_grad=True), torch.zeros(4, dtype=torch.long))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        fv.LEAM()(torch.randn(2, 18, 512))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# data parallel host logic on gloo, world_size 2
+# ----------------------------------------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dp_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fer_vit_b200.parallel import GradBucketer, global_ce_denominator, sync_parameters
+    b = GradBucketer(num_buckets=3)
+    groups = b.stage_groups(14)                      # ViT-B: head + 12 blocks + input stage
+    assert groups[0][0] == 0 and groups[-1][1] == 14 and all(a[1] == c[0] for a, c in zip(groups, groups[1:]))
+    # a fake flat gradient buffer in backward order, reduced bucket by bucket like PlanRunner.backward does
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    bounds = [0, 300, 650, 1000]
+    for lo, hi in zip(bounds, bounds[1:]):
+        b.reduce_async(flat[lo:hi])
+    b.finish()
+    expect = torch.arange(1000, dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+    ok = torch.allclose(flat, expect)
+    # parameters broadcast from rank 0
+    lin = torch.nn.Linear(4, 3)
+    with torch.no_grad():
+        lin.weight.fill_(float(rank + 1))
+    sync_parameters(lin)
+    ok = ok and bool((lin.weight == 1.0).all())
+    # class-weighted CE: local denominator = global sum / world
+    w = torch.tensor([1.0, 2.0, 3.0])
+    labels = torch.tensor([0, 1]) if rank == 0 else torch.tensor([2, 2])
+    den = global_ce_denominator(labels, w)
+    ok = ok and abs(den.item() - (1 + 2 + 3 + 3) / world) < 1e-6
+    ok = ok and b.calls == 3 and b.bytes_reduced == 4000
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_grad_bucketer_gloo_world_size_2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out[0] and out[1]
+
+
+def test_weighted_ce_is_rank_invariant_under_dp():
+    """Oracle-level check of the DP rule: averaging the per-rank gradients computed with den = global/world equals
+    the single-process gradient of the class-weighted mean loss."""
+    from oracle import reference_math as R
+    torch.manual_seed(0)
+    z = torch.randn(8, 7, dtype=torch.float64, requires_grad=True)
+    y = torch.randint(0, 7, (8,))
+    w = torch.rand(7, dtype=torch.float64) + 0.5
+    full, = torch.autograd.grad(R.cross_entropy(z, y, w), z)
+    den_local = w[y].sum() / 2
+    parts = []
+    for sl in (slice(0, 4), slice(4, 8)):
+        zz = z[sl].detach().requires_grad_(True)
+        lp = torch.log_softmax(zz, -1)
+        loss = -(lp[torch.arange(4), y[sl]] * w[y[sl]]).sum() / den_local
+        parts.append(torch.autograd.grad(loss, zz)[0] / 2)    # all-reduce AVG
+    assert torch.allclose(torch.cat(parts), full, atol=1e-12)
