@@ -75,6 +75,19 @@ FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, co
   return gemm_bf16_tc((const bf16*)x, K, false, (const bf16*)W, K, false, M, N, K, 1, force_bn, e, S_(stream));
 }
 
+FV_API int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const void* aux, const float* residual,
+                               int M, int N, int K, int act, void* out, float* out_f32, int force_bn, void* stream) {
+  FV_CHECK(dy && Wt, "linear_dgrad: null argument");
+  FV_CHECK(act == ACT_NONE || aux != nullptr, "linear_dgrad: aux (pre-activation) is required with an activation");
+  Epilogue e = make_epilogue();
+  e.residual = residual; e.act_bwd = act; e.aux = aux; e.out = out; e.out_f32 = out_f32; e.ldo = K;
+  // GEMM view: rows M, output columns K, reduction over N; B operand = Wt [K, N]
+  if (act_dtype == FERVIT_F32)
+    return gemm_f32_simt((const float*)dy, N, 1, (const float*)Wt, N, 1, M, K, N, 1, e, S_(stream));
+  FV_CHECK(act_dtype == FERVIT_BF16, "linear_dgrad: unknown dtype %d", act_dtype);
+  return gemm_bf16_tc((const bf16*)dy, N, false, (const bf16*)Wt, N, false, M, K, N, 1, force_bn, e, S_(stream));
+}
+
 static int op_wgrad_splits(int act_dtype, int M, int N, int K) {
   // same policy as the plan (plan.cu: wgrad_splits), restated on the public shapes: dW[N,K] reduced over M rows
   const int sms = num_sms();

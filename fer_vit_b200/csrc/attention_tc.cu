@@ -1,9 +1,10 @@
 // Short-sequence attention on tensor cores for S <= 32 (19 w+ tokens + cls): one warp owns one (sample, head).
-// Q.K^T, P.V and the five backward products are 16x8x16 bf16 MMAs (mma.sync) on fragments loaded straight from
-// global memory; softmax runs on the accumulator fragments with quad shuffles; only the operands needed in
-// transposed form (V for P.V; K, Q, dO for the backward products) are staged through shared memory.
-// The whole problem is 19x64 per operand, far below a tcgen05 tile (M = 128), so the legacy warp-level MMA is the
-// right-sized instruction here; the kernel is bound by its HBM/L2 traffic (~9.5 flop/B).
+// Q, K, V (and dO) of the head are staged ONCE into shared memory with coalesced 16-byte loads (rows beyond S
+// zero-filled); every MMA operand — including the transposed ones (V for P.V; K, Q, dO for the backward products) —
+// is then fetched with ldmatrix / ldmatrix.trans, so nothing is stored transposed. Q.K^T, P.V and the five backward
+// products are 16x8x16 bf16 MMAs (mma.sync); softmax runs on the accumulator fragments with quad shuffles.
+// A 19x64 problem is far below a tcgen05 tile (M = 128), so the warp-level MMA is the right-sized instruction; the
+// kernel is bound by its HBM/L2 traffic (~9.5 flop/B).
 //
 // qkv layout: [B*S, 3E], columns [Q | K | V], head h at columns h*HD (timm qkv / torch in_proj packing).
 #include "common.cuh"
@@ -14,53 +15,51 @@ namespace fervit {
 namespace attn_tc {
 
 constexpr int WARPS = 4;
-constexpr int SP = 32;        // padded sequence
-constexpr int LDT = SP + 8;   // row stride (elements) of a transposed [HD][SP] operand in smem: conflict-free LDS.32
+constexpr int SP = 32;  // padded sequence
 
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+template <int HD> struct Lay { static constexpr int LD = HD + 8; };  // row stride (elements): conflict-free ldmatrix
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-
-// 32-bit load of two consecutive bf16 of row `r` (zero beyond S rows)
-__device__ __forceinline__ uint32_t ld2(const bf16* __restrict__ base, size_t row_stride, int r, int c, int S) {
-  return r < S ? __ldg(reinterpret_cast<const unsigned int*>(base + (size_t)r * row_stride + c)) : 0u;
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
 }
-// A fragment (16x16, row-major source): m-tile mt, k-step ks
-__device__ __forceinline__ void load_a(uint32_t (&a)[4], const bf16* __restrict__ base, size_t rs, int mt, int ks, int g,
-                                       int q, int S) {
-  const int r0 = mt * 16 + g, c0 = ks * 16 + 2 * q;
-  a[0] = ld2(base, rs, r0, c0, S);
-  a[1] = ld2(base, rs, r0 + 8, c0, S);
-  a[2] = ld2(base, rs, r0, c0 + 8, S);
-  a[3] = ld2(base, rs, r0 + 8, c0 + 8, S);
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
 }
-// B fragment (16x8, "col"): B[k][n] = M[n][k] with M row-major: n-tile nt, k-step ks
-__device__ __forceinline__ void load_b(uint32_t (&b)[2], const bf16* __restrict__ base, size_t rs, int nt, int ks, int g,
-                                       int q, int S) {
-  const int n = nt * 8 + g, c0 = ks * 16 + 2 * q;
-  b[0] = ld2(base, rs, n, c0, S);
-  b[1] = ld2(base, rs, n, c0 + 8, S);
+// A fragment of rows [mt*16, +16), k in [ks*16, +16) of a row-major smem matrix M[row][k]
+template <int LD>
+__device__ __forceinline__ void lda(uint32_t (&a)[4], const bf16* M, int mt, int ks, int lane) {
+  ldsm_x4(a, M + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8);
 }
-// B fragment from a transposed smem operand T[HD][LDT] (T[d][j] = M[j][d]): B[k=j][n=d], n-tile nt (over d), k-step ks (over j)
-__device__ __forceinline__ void load_bt(uint32_t (&b)[2], const bf16* T, int nt, int ks, int g, int q) {
-  const bf16* p = T + (nt * 8 + g) * LDT + ks * 16 + 2 * q;
-  b[0] = *reinterpret_cast<const uint32_t*>(p);
-  b[1] = *reinterpret_cast<const uint32_t*>(p + 8);
+// B fragments of TWO n-tiles (n in [np*16, +16)), k in [ks*16, +16), from M[n][k] (k contiguous): r[0..1] tile 2np, r[2..3] tile 2np+1
+template <int LD>
+__device__ __forceinline__ void ldb(uint32_t (&r)[4], const bf16* M, int np, int ks, int lane) {
+  ldsm_x4(r, M + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
 }
-// stage M[S][HD] (global, row stride rs) transposed into T[HD][LDT], zero-filling columns S..31
+// B fragments of TWO n-tiles from M[k][n] (n contiguous): k in [kk*16, +16), n in [np*16, +16)
+template <int LD>
+__device__ __forceinline__ void ldbt(uint32_t (&r)[4], const bf16* M, int np, int kk, int lane) {
+  ldsm_x4_t(r, M + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + np * 16 + (lane >> 4) * 8);
+}
+// stage M[S][HD] (global, row stride rs) into smem [32][LD], zero-filling rows S..31
 template <int HD>
-__device__ __forceinline__ void stage_t(bf16* T, const bf16* __restrict__ base, size_t rs, int S, int lane) {
-  constexpr int CH = HD / 8;
+__device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, size_t rs, int S, int lane) {
+  constexpr int CH = HD / 8, LD = Lay<HD>::LD;
+#pragma unroll 2
   for (int i = lane; i < SP * CH; i += 32) {
-    const int j = i / CH, d0 = (i % CH) * 8;
+    const int r = i / CH, c = (i % CH) * 8;
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (j < S) v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)j * rs + d0));
-    const bf16* e = reinterpret_cast<const bf16*>(&v);
-#pragma unroll
-    for (int t = 0; t < 8; ++t) T[(d0 + t) * LDT + j] = e[t];
+    if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * rs + c));
+    *reinterpret_cast<uint4*>(dst + r * LD + c) = v;
   }
 }
 
@@ -68,8 +67,9 @@ template <int HD>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int B, int S, int H,
                    float scale, Dropout drop) {
-  __shared__ __align__(16) bf16 smem_vt[WARPS][HD * LDT];
-  constexpr int KS = HD / 16, ND = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
+  constexpr int MAT = SP * LD;  // elements per staged matrix
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.x * WARPS + warp;
@@ -78,10 +78,12 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
   const int E = H * HD;
   const size_t rs = (size_t)3 * E;
   const bf16* Qg = qkv + (size_t)b * S * rs + h * HD;
-  const bf16* Kg = Qg + E;
-  const bf16* Vg = Qg + 2 * E;
-  bf16* Vt = smem_vt[warp];
-  stage_t<HD>(Vt, Vg, rs, S, lane);
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 3 * MAT;
+  bf16* Ks = Qs + MAT;
+  bf16* Vs = Ks + MAT;
+  stage<HD>(Qs, Qg, rs, S, lane);
+  stage<HD>(Ks, Qg + E, rs, S, lane);
+  stage<HD>(Vs, Qg + 2 * E, rs, S, lane);
   __syncwarp();
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
 #pragma unroll 1
@@ -95,12 +97,13 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t a[4];
-      load_a(a, Qg, rs, mt, ks, g, q, S);
+      lda<LD>(a, Qs, mt, ks, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bb[2];
-        load_b(bb, Kg, rs, nt, ks, g, q, S);
-        mma16816(c[nt], a, bb);
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bb[4];
+        ldb<LD>(bb, Ks, np, ks, lane);
+        mma16816(c[2 * np], a, bb[0], bb[1]);
+        mma16816(c[2 * np + 1], a, bb[2], bb[3]);
       }
     }
     // softmax over keys for rows r0 = mt*16+g (elements 0,1) and r1 = r0+8 (elements 2,3)
@@ -161,10 +164,11 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
       a[2] = pack_bf16x2(c[2 * kk + 1][0] * inv[0], c[2 * kk + 1][1] * inv[0]);
       a[3] = pack_bf16x2(c[2 * kk + 1][2] * inv[1], c[2 * kk + 1][3] * inv[1]);
 #pragma unroll
-      for (int nd = 0; nd < ND; ++nd) {
-        uint32_t bb[2];
-        load_bt(bb, Vt, nd, kk, g, q);
-        mma16816(o[nd], a, bb);
+      for (int np = 0; np < ND / 2; ++np) {
+        uint32_t bb[4];
+        ldbt<LD>(bb, Vs, np, kk, lane);
+        mma16816(o[2 * np], a, bb[0], bb[1]);
+        mma16816(o[2 * np + 1], a, bb[2], bb[3]);
       }
     }
     bf16* Og = out + (size_t)b * S * E + h * HD;
@@ -185,8 +189,9 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
                    const float* __restrict__ lse, bf16* __restrict__ dqkv, int B, int S, int H, float scale,
                    Dropout drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int KS = HD / 16, ND = HD / 8;
-  constexpr int PER_WARP = 3 * HD * LDT * 2 + 2 * SP * 4;   // Kt, Qt, dOt (bf16) + LSE, D (fp32)
+  constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
+  constexpr int MAT = SP * LD;
+  constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4;   // Q, K, V, dO (bf16) + LSE, D (fp32), bytes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.x * WARPS + warp;
@@ -195,18 +200,18 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   const int E = H * HD;
   const size_t rs = (size_t)3 * E;
   const bf16* Qg = qkv + (size_t)b * S * rs + h * HD;
-  const bf16* Kg = Qg + E;
-  const bf16* Vg = Qg + 2 * E;
   const bf16* Og = out + (size_t)b * S * E + h * HD;
   const bf16* dOg = dout + (size_t)b * S * E + h * HD;
-  bf16* Kt = reinterpret_cast<bf16*>(smem_raw + (size_t)warp * PER_WARP);
-  bf16* Qt = Kt + HD * LDT;
-  bf16* dOt = Qt + HD * LDT;
-  float* Ls = reinterpret_cast<float*>(dOt + HD * LDT);
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw + (size_t)warp * PER_WARP);
+  bf16* Ks = Qs + MAT;
+  bf16* Vs = Ks + MAT;
+  bf16* dOs = Vs + MAT;
+  float* Ls = reinterpret_cast<float*>(dOs + MAT);
   float* Ds = Ls + SP;
-  stage_t<HD>(Kt, Kg, rs, S, lane);
-  stage_t<HD>(Qt, Qg, rs, S, lane);
-  stage_t<HD>(dOt, dOg, (size_t)E, S, lane);
+  stage<HD>(Qs, Qg, rs, S, lane);
+  stage<HD>(Ks, Qg + E, rs, S, lane);
+  stage<HD>(Vs, Qg + 2 * E, rs, S, lane);
+  stage<HD>(dOs, dOg, (size_t)E, S, lane);
   {
     // D_i = dO_i . O_i ; rows beyond S get LSE = +inf so their probabilities vanish
     float dsum = 0.f;
@@ -245,15 +250,17 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t aq[4], ad[4];
-      load_a(aq, Qg, rs, mt, ks, g, q, S);
-      load_a(ad, dOg, (size_t)E, mt, ks, g, q, S);
+      lda<LD>(aq, Qs, mt, ks, lane);
+      lda<LD>(ad, dOs, mt, ks, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bk[2], bv[2];
-        load_b(bk, Kg, rs, nt, ks, g, q, S);
-        load_b(bv, Vg, rs, nt, ks, g, q, S);
-        mma16816(c[nt], aq, bk);
-        mma16816(dp[nt], ad, bv);
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bk[4], bv[4];
+        ldb<LD>(bk, Ks, np, ks, lane);
+        ldb<LD>(bv, Vs, np, ks, lane);
+        mma16816(c[2 * np], aq, bk[0], bk[1]);
+        mma16816(c[2 * np + 1], aq, bk[2], bk[3]);
+        mma16816(dp[2 * np], ad, bv[0], bv[1]);
+        mma16816(dp[2 * np + 1], ad, bv[2], bv[3]);
       }
     }
     const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -284,10 +291,11 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
       a[2] = pack_bf16x2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
       a[3] = pack_bf16x2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
 #pragma unroll
-      for (int nd = 0; nd < ND; ++nd) {
-        uint32_t bb[2];
-        load_bt(bb, Kt, nd, kk, g, q);
-        mma16816(dq[nd], a, bb);
+      for (int np = 0; np < ND / 2; ++np) {
+        uint32_t bb[4];
+        ldbt<LD>(bb, Ks, np, kk, lane);
+        mma16816(dq[2 * np], a, bb[0], bb[1]);
+        mma16816(dq[2 * np + 1], a, bb[2], bb[3]);
       }
     }
 #pragma unroll
@@ -310,15 +318,17 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       uint32_t ak[4], av[4];
-      load_a(ak, Kg, rs, mt, ks, g, q, S);
-      load_a(av, Vg, rs, mt, ks, g, q, S);
+      lda<LD>(ak, Ks, mt, ks, lane);
+      lda<LD>(av, Vs, mt, ks, lane);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bq[2], bd[2];
-        load_b(bq, Qg, rs, nt, ks, g, q, S);
-        load_b(bd, dOg, (size_t)E, nt, ks, g, q, S);
-        mma16816(c[nt], ak, bq);
-        mma16816(dp[nt], av, bd);
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bq[4], bd[4];
+        ldb<LD>(bq, Qs, np, ks, lane);
+        ldb<LD>(bd, dOs, np, ks, lane);
+        mma16816(c[2 * np], ak, bq[0], bq[1]);
+        mma16816(c[2 * np + 1], ak, bq[2], bq[3]);
+        mma16816(dp[2 * np], av, bd[0], bd[1]);
+        mma16816(dp[2 * np + 1], av, bd[2], bd[3]);
       }
     }
     const int j0 = mt * 16 + g, j1 = j0 + 8;
@@ -356,12 +366,14 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
       as[2] = pack_bf16x2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
       as[3] = pack_bf16x2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
 #pragma unroll
-      for (int nd = 0; nd < ND; ++nd) {
-        uint32_t bo[2], bq[2];
-        load_bt(bo, dOt, nd, kk, g, q);
-        load_bt(bq, Qt, nd, kk, g, q);
-        mma16816(dv[nd], ap, bo);
-        mma16816(dk[nd], as, bq);
+      for (int np = 0; np < ND / 2; ++np) {
+        uint32_t bo[4], bq[4];
+        ldbt<LD>(bo, dOs, np, kk, lane);
+        ldbt<LD>(bq, Qs, np, kk, lane);
+        mma16816(dv[2 * np], ap, bo[0], bo[1]);
+        mma16816(dv[2 * np + 1], ap, bo[2], bo[3]);
+        mma16816(dk[2 * np], as, bq[0], bq[1]);
+        mma16816(dk[2 * np + 1], as, bq[2], bq[3]);
       }
     }
 #pragma unroll
@@ -382,8 +394,14 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 template <int HD>
 int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, Dropout drop, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)HD);
+  constexpr int smem = WARPS * 3 * SP * Lay<HD>::LD * 2;
+  static bool attr = false;
+  if (!attr && smem > 48 * 1024) {
+    FV_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
   ProfScope prof(1, (double)B * S * H * HD * 4.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  attn_tc_fwd_kernel<HD><<<ceil_div(B * H, WARPS), WARPS * 32, 0, stream>>>(qkv, out, lse, B, S, H, scale, drop);
+  attn_tc_fwd_kernel<HD><<<ceil_div(B * H, WARPS), WARPS * 32, smem, stream>>>(qkv, out, lse, B, S, H, scale, drop);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -392,7 +410,7 @@ template <int HD>
 int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
                Dropout drop, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)HD);
-  constexpr int smem = WARPS * (3 * HD * LDT * 2 + 2 * SP * 4);
+  constexpr int smem = WARPS * (4 * SP * Lay<HD>::LD * 2 + 2 * SP * 4);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     FV_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

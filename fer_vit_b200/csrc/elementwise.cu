@@ -113,30 +113,65 @@ __global__ void gather_tokens_kernel(const float* __restrict__ dx0, AT* __restri
 }
 
 // ---- deterministic column sum: in [R, C] (row stride ld) -> partial [chunks][C] -> out [C] ----
+// block (32, 8): x = group of 4 columns, y = row lane; every thread keeps 8 independent 16-byte loads in flight,
+// the 8 row lanes are combined through shared memory in a fixed order.
+__device__ __forceinline__ float4 colsum_block_reduce(float4 acc, float4 (*red)[32]) {
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const float4 v = red[y][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+  }
+  return t;
+}
 template <typename T>
-__global__ void colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int rows_per_chunk,
-                                      float* __restrict__ partial, Dropout drop) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int rows_per_chunk,
+                      float* __restrict__ partial, Dropout drop) {
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_chunk;
   const int r1 = min(R, r0 + rows_per_chunk);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    float v = to_f32<T>(in[(size_t)r * ld + c]);
-    if (drop.threshold)
-      v = drop_keep(drop.eff(), drop.site, (uint64_t)r * ld + c, drop.threshold) ? v * drop.scale : 0.f;
-    s += v;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll 8
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+      float4 v = load4<T>(in + (size_t)r * ld + c);
+      if (drop.threshold) {
+        const uint64_t base = (uint64_t)r * ld + c, seed = drop.eff();
+        v.x = drop_keep(seed, drop.site, base + 0, drop.threshold) ? v.x * drop.scale : 0.f;
+        v.y = drop_keep(seed, drop.site, base + 1, drop.threshold) ? v.y * drop.scale : 0.f;
+        v.z = drop_keep(seed, drop.site, base + 2, drop.threshold) ? v.z * drop.scale : 0.f;
+        v.w = drop_keep(seed, drop.site, base + 3, drop.threshold) ? v.w * drop.scale : 0.f;
+      }
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  partial[(size_t)blockIdx.y * C + c] = s;
+  const float4 t = colsum_block_reduce(acc, red);
+  if (threadIdx.y == 0 && c < C) *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * C + c) = t;
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const float* alpha_ptr,
-                                    float alpha, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += partial[(size_t)k * C + c];
-  if (alpha_ptr) alpha *= __ldg(alpha_ptr);
-  out[c] = s * alpha;
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const float* alpha_ptr, float alpha,
+                    float* __restrict__ out) {
+  __shared__ float4 red[8][32];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll 4
+    for (int k = threadIdx.y; k < chunks; k += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)k * C + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  const float4 t = colsum_block_reduce(acc, red);
+  if (threadIdx.y == 0 && c < C) {
+    if (alpha_ptr) alpha *= __ldg(alpha_ptr);
+    *reinterpret_cast<float4*>(out + c) = make_float4(t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha);
+  }
 }
 
 // ---- split-K reduction: out[i] = alpha * sum_s partial[s][i] ----
@@ -145,6 +180,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   if (alpha_ptr) alpha *= __ldg(alpha_ptr);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
     for (int s = 0; s < splits; ++s) {
       const float4 v = *reinterpret_cast<const float4*>(partial + ((size_t)s * n4 + i) * 4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
@@ -305,12 +341,13 @@ int colsum_chunks(int R) {
 template <typename T>
 int colsum(const T* in, int R, int C, long long ld, float* scratch, const float* alpha_ptr, float alpha, float* out,
            Dropout drop, cudaStream_t stream) {
+  FV_CHECK(C % 4 == 0 && ld % 4 == 0, "colsum: column count and leading dimension must be multiples of 4");
   const int chunks = colsum_chunks(R);
   const int rpc = ceil_div(R, chunks);
-  dim3 grid(ceil_div(C, 128), chunks);
-  ew::colsum_partial_kernel<T><<<grid, 128, 0, stream>>>(in, R, C, ld, rpc, scratch, drop);
+  dim3 grid(ceil_div(C, 128), chunks), block(32, 8);
+  ew::colsum_partial_kernel<T><<<grid, block, 0, stream>>>(in, R, C, ld, rpc, scratch, drop);
   FV_COUNT_LAUNCH();
-  ew::colsum_final_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(scratch, chunks, C, alpha_ptr, alpha, out);
+  ew::colsum_final_kernel<<<ceil_div(C, 128), block, 0, stream>>>(scratch, chunks, C, alpha_ptr, alpha, out);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -321,7 +358,8 @@ template int colsum<bf16>(const bf16*, int, int, long long, float*, const float*
                           cudaStream_t);
 
 int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream) {
-  ew::colsum_final_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(partial, chunks, C, nullptr, 1.0f, out);
+  FV_CHECK(C % 4 == 0, "colsum_reduce_partials: column count must be a multiple of 4");
+  ew::colsum_final_kernel<<<ceil_div(C, 128), dim3(32, 8), 0, stream>>>(partial, chunks, C, nullptr, 1.0f, out);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -330,7 +368,7 @@ int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, 
 int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
                   cudaStream_t stream) {
   FV_CHECK(n % 4 == 0, "splitk_reduce: element count must be a multiple of 4");
-  ew::splitk_reduce_kernel<<<ew::grid_for(n / 4, 256), 256, 0, stream>>>(partial, splits, n / 4, alpha_ptr, alpha, out);
+  ew::splitk_reduce_kernel<<<ew::grid_for(n / 4, 64), 64, 0, stream>>>(partial, splits, n / 4, alpha_ptr, alpha, out);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

@@ -11,7 +11,7 @@ namespace fervit {
 
 enum EpiKind {
   EPK_PLAIN = 0,     // bias / alpha / residual / outputs only
-  EPK_GELU,          // + forward GELU (pre-activation optionally stored)
+  EPK_GELU,          // + forward GELU (pre-activation optionally stored); fast erf (common.cuh), bf16 kernels only
   EPK_RELU,          // + forward ReLU
   EPK_GELU_BWD,      // accumulator times GELU'(aux)
   EPK_RELU_BWD,      // accumulator times ReLU'(aux)
@@ -34,9 +34,11 @@ static inline int epilogue_kind(const Epilogue& e) {
 
 // Apply the epilogue to NV consecutive columns [col, col+NV) of logical row `row`.
 // Caller guarantees row < M and col + NV <= N, NV % 4 == 0 and col % 4 == 0.
+// pre_aux / pre_res: side inputs the caller already fetched (software-pipelined epilogues, NV == 4); nullptr = load here.
 template <typename AT, int NV, int KIND>
 __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, int row, int col, int N,
-                                               float (&v)[NV]) {
+                                               float (&v)[NV], const float4* pre_aux = nullptr,
+                                               const float4* pre_res = nullptr) {
   constexpr bool GEN = (KIND == EPK_GENERIC);
   if (e.bias) {
 #pragma unroll
@@ -49,13 +51,13 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
     const AT* aux = reinterpret_cast<const AT*>(e.aux) + (size_t)row * N + col;
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
-      const float4 a = load4<AT>(aux + i);
+      const float4 a = pre_aux ? *pre_aux : load4<AT>(aux + i);
       const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         float d;
         if (GEN) d = act_bwd(e.act_bwd, av[t]);
-        else if (KIND == EPK_GELU_BWD) d = gelu_bwd(av[t]);
+        else if (KIND == EPK_GELU_BWD) d = gelu_bwd_fast(av[t]);
         else d = av[t] > 0.0f ? 1.0f : 0.0f;
         v[i + t] *= d;
       }
@@ -72,7 +74,7 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       if (GEN) v[i] = act_fwd(e.act, v[i]);
-      else if (KIND == EPK_GELU) v[i] = gelu_fwd(v[i]);
+      else if (KIND == EPK_GELU) v[i] = gelu_fwd_fast(v[i]);
       else v[i] = fmaxf(v[i], 0.0f);
     }
   }
@@ -103,7 +105,7 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
   if (e.residual) {
 #pragma unroll
     for (int i = 0; i < NV; i += 4) {
-      const float4 r = *reinterpret_cast<const float4*>(e.residual + ooff + i);
+      const float4 r = pre_res ? *pre_res : *reinterpret_cast<const float4*>(e.residual + ooff + i);
       v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
     }
   }
@@ -118,6 +120,15 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
     for (int i = 0; i < NV; i += 4)
       *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   }
+}
+
+// Fetch the side inputs of one 4-column group ahead of time (plain row mapping only: KIND != REMAP/GENERIC-remap).
+template <typename AT, int KIND>
+__device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int row, int col, int N, float4& aux, float4& res) {
+  constexpr bool GEN = (KIND == EPK_GENERIC);
+  if (GEN ? (e.act_bwd != ACT_NONE) : (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD))
+    aux = load4<AT>(reinterpret_cast<const AT*>(e.aux) + (size_t)row * N + col);
+  if (e.residual) res = *reinterpret_cast<const float4*>(e.residual + (size_t)row * e.ldo + col);
 }
 
 }  // namespace fervit

@@ -308,14 +308,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * COLS_PER_WARP);
       float* stg = epi_stage + (warp - 4) * (32 * C::EPI_LD);
+      // Side inputs (residual, activation-derivative operand) are software-pipelined one 16-column chunk ahead, so
+      // their global-load latency overlaps the TMEM load / transposition / math of the current chunk.
+      constexpr bool PIPE = (KIND != EPK_REMAP && KIND != EPK_GENERIC);
+      const int rl = lane >> 2, c4 = (lane & 3) * 4;
+      const int col_base = n_blk * BN + half * COLS_PER_WARP;
+      float4 aux_nx[4], res_nx[4];
+      if (PIPE && col_base < p.N) {
+#pragma unroll
+        for (int itr = 0; itr < 4; ++itr)
+          if (row0 + itr * 8 + rl < p.M)
+            epilogue_prefetch<bf16, KIND>(e, row0 + itr * 8 + rl, col_base + c4, p.N, aux_nx[itr], res_nx[itr]);
+      }
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 16) {
-        const int col = n_blk * BN + half * COLS_PER_WARP + c;
+        const int col = col_base + c;
         if (col >= p.N) break;  // warp-uniform
         if (p.debug & 4) break;
         float v[16];
         tmem_ld16(taddr0 + (uint32_t)c, v);
         if (p.debug & 8) continue;
+        float4 aux_cur[4], res_cur[4];
+        if (PIPE) {
+#pragma unroll
+          for (int itr = 0; itr < 4; ++itr) { aux_cur[itr] = aux_nx[itr]; res_cur[itr] = res_nx[itr]; }
+          if (c + 16 < COLS_PER_WARP && col + 16 < p.N) {
+#pragma unroll
+            for (int itr = 0; itr < 4; ++itr)
+              if (row0 + itr * 8 + rl < p.M)
+                epilogue_prefetch<bf16, KIND>(e, row0 + itr * 8 + rl, col + 16 + c4, p.N, aux_nx[itr], res_nx[itr]);
+          }
+        }
         // TMEM hands each lane one ROW of the tile; global memory wants lanes side by side along a row.
         // Transpose the 32x16 chunk through shared memory so every epilogue load/store below is coalesced.
 #pragma unroll
@@ -324,11 +347,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         __syncwarp();
 #pragma unroll
         for (int itr = 0; itr < 4; ++itr) {
-          const int r = itr * 8 + (lane >> 2), c4 = (lane & 3) * 4;
+          const int r = itr * 8 + rl;
           const float4 w = *reinterpret_cast<const float4*>(stg + r * C::EPI_LD + c4);
           float w4[4] = {w.x, w.y, w.z, w.w};
           if (p.debug & 32) { if (w4[0] == 1.2345e30f) e.out_f32[0] = w4[1]; continue; }
-          if (row0 + r < p.M) epilogue_apply<bf16, 4, KIND>(e, alpha, row0 + r, col + c4, p.N, w4);
+          if (row0 + r < p.M) {
+            if (PIPE) epilogue_apply<bf16, 4, KIND>(e, alpha, row0 + r, col + c4, p.N, w4, &aux_cur[itr], &res_cur[itr]);
+            else epilogue_apply<bf16, 4, KIND>(e, alpha, row0 + r, col + c4, p.N, w4);
+          }
         }
         __syncwarp();
       }
@@ -449,16 +475,22 @@ int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool
   p.splits = ceil_div(total_kb, p.kb_per_split);
   p.epi = epi;
   {
+    // timing experiments only (tools/gemm_bench.py): re-read per call when the variable existed at the first call
     static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("FERVIT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.debug = dbg;
+    if (dbg != 0) { const char* e = getenv("FERVIT_GEMM_DEBUG"); dbg = e ? (atoi(e) | (1 << 30)) : 0; }
+    p.debug = dbg & ~(1 << 30);
   }
   if (p.splits > 1)
     FV_CHECK(epi.out_f32 != nullptr && epi.out == nullptr && epi.bias == nullptr && epi.residual == nullptr &&
                  epi.act == 0 && epi.act_bwd == 0 && epi.out_pre == nullptr && epi.remap_L == 0 && epi.ldo == N,
              "gemm_bf16_tc: split-K supports only a plain fp32 partial output");
-  int bn = force_bn > 0 ? force_bn : tc::choose_bn(M, N, p.kb_per_split, p.splits);
   const int kind = epilogue_kind(epi);
+  // forward / dgrad shapes go to the CTA-pair kernel (gemm_tc2.cu); this single-CTA kernel keeps the MN-major
+  // (wgrad), split-K, row-remapping and dropout epilogues
+  if (!a_mn && !b_mn && p.splits == 1 && force_bn >= 0 && gemm_bf16_tc2_supported(M, N, K, lda, ldb, epi, kind))
+    return gemm_bf16_tc2(A, lda, B, ldb, M, N, K, force_bn, epi, kind, stream);
+  if (force_bn < 0) force_bn = -force_bn;  // negative: force this kernel with that tile width (benchmarks)
+  int bn = force_bn > 0 ? force_bn : tc::choose_bn(M, N, p.kb_per_split, p.splits);
   if (a_mn != b_mn) { set_error("gemm_bf16_tc: mixed operand major-ness is not instantiated"); return 1; }
 #define FV_TC_KIND(BN_, K_) case K_: return tc::launch<BN_, false, false, K_>(A, lda, B, ldb, p, stream);
 #define FV_TC_DISPATCH(BN_)                                                                  \

@@ -1,0 +1,480 @@
+// bf16 GEMM on the 5th-generation tensor cores, CTA-pair edition (the forward / dgrad workhorse).
+//
+//   C[M,N] (+ fused epilogue) = A[M,K] · B[N,K]^T       A, B bf16 row-major ("K-major"), fp32 accumulation
+//
+// Two CTAs of one cluster (one TPC) cooperate on a 256 x BN tile with `tcgen05.mma.cta_group::2` (M = 256):
+// each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 rows), so the L2 -> shared-memory traffic and
+// the shared-memory read bandwidth per FLOP drop by a third against a lone CTA on a 128 x BN tile (measured on B200:
+// the single-CTA kernel's TMA traffic alone ran at 90 % of its MMA time; see DESIGN.md / profiles/gemm_sweep_r1d).
+// Each CTA holds its 128 x BN fp32 accumulator slice in its own TMEM, double-buffered, so the epilogue of tile i
+// overlaps the MMAs of tile i+1. Persistent: one CTA pair per TPC, static round-robin tile schedule.
+//
+//   warp 0      TMA producer (one lane, both CTAs; completion bytes of both CTAs land on the leader's mbarrier)
+//   warp 1      MMA issuer   (one lane, leader CTA only; commits multicast to both CTAs' barriers)
+//   warp 2      TMEM allocator / deallocator
+//   warps 4..11 epilogue: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4
+//
+// Epilogue: all global traffic goes through TMA. Per 32-column chunk a thread owns one accumulator row
+// (tcgen05.ld 32x32b.x32), applies bias / activation / activation-derivative / alpha / residual in registers, writes
+// the results into swizzled per-warp staging tiles and one lane issues `cp.async.bulk.tensor` stores (bf16 tiles
+// SWIZZLE_64B, fp32 tiles SWIZZLE_128B: conflict-free 16-byte row writes). Side inputs (fp32 residual, bf16
+// pre-activation for GELU'/ReLU') are TMA-loaded into the same staging tiles two chunks ahead. M / N tails are
+// clipped (stores) or zero-filled (loads) by the TMA unit: no per-element predicates anywhere.
+//
+// Replaces the cuBLAS calls behind nn.Linear / F.linear in the reference's blocks (timm Block via
+// hybrid_latent_vit.py:227-233; nn.TransformerEncoderLayer via latent_vit.py:24-31; AdapterModule :264-265).
+#include "common.cuh"
+#include "kernels.h"
+#include "epilogue.cuh"
+#include "tc_ptx.cuh"
+#include <stdlib.h>
+
+namespace fervit {
+namespace tc2 {
+
+using namespace ptx;
+
+constexpr int BM = 128;  // rows per CTA; the pair covers 256
+constexpr int BK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 128 + EPI_WARPS * 32;
+constexpr int CHUNK = 32;            // epilogue columns per step
+constexpr int XT = 32 * CHUNK * 4;   // fp32 staging tile: 32 rows x 128 B
+constexpr int YT = 32 * CHUNK * 2;   // bf16 staging tile: 32 rows x 64 B
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
+
+template <int BN, int KIND, bool F32>
+struct Cfg {
+  static constexpr bool FWD_ACT = (KIND == EPK_GELU || KIND == EPK_RELU);
+  static constexpr bool BWD_ACT = (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int X_BYTES = F32 ? 2 * XT : 0;                    // fp32 out / residual in (in place), x2
+  static constexpr int Y_BYTES = 2 * YT;                              // bf16 out, x2
+  static constexpr int Z_BYTES = (FWD_ACT || BWD_ACT) ? 2 * YT : 0;   // bf16 pre-activation out / in, x2
+  static constexpr int WARP_STAGING = X_BYTES + Y_BYTES + Z_BYTES;
+  static constexpr int STAGING = EPI_WARPS * WARP_STAGING;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - STAGING;
+  static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers; 256 or 512 (powers of two)
+  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(2 * STAGES + 4 + 2 * EPI_WARPS + 1 <= BAR_BYTES / 8, "barrier area too small");
+};
+
+struct Params {
+  int M, N, K;
+  int pair_m_blocks, n_blocks;
+  const float* bias;
+  const float* alpha_ptr;
+  float alpha;
+  int has_out, has_z, has_f32, has_res;
+};
+
+template <int BN, int KIND, bool F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
+                const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_r, const Params p) {
+  using C = Cfg<BN, KIND, F32>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
+  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::STAGING);
+  uint64_t* full_bar = bars;                         // [STAGES]   leader's is the live one
+  uint64_t* empty_bar = bars + C::STAGES;            // [STAGES]   per CTA
+  uint64_t* tmem_full = bars + 2 * C::STAGES;        // [2]        per CTA
+  uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;   // [2]        leader's is the live one
+  uint64_t* ld_bar = bars + 2 * C::STAGES + 4;       // [EPI_WARPS][2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 2 * EPI_WARPS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int units = p.pair_m_blocks * p.n_blocks;
+  const int total_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_b);
+    if (p.has_out) prefetch_tmap(&tm_y);
+    if (p.has_z) prefetch_tmap(&tm_z);
+    if (p.has_f32) prefetch_tmap(&tm_x);
+    if (p.has_res) prefetch_tmap(&tm_r);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 2 * EPI_WARPS);  // the epilogue warps of BOTH CTAs
+    }
+    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&ld_bar[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_base_slot, (uint32_t)C::TMEM_COLS);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = pair_id; u < units; u += num_pairs) {
+        const int pm = u % p.pair_m_blocks;
+        const int n_blk = u / p.pair_m_blocks;
+        const int row_a = pm * (2 * BM) + (int)rank * BM;
+        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1, 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          const uint32_t full0 = mapa(smem_u32(&full_bar[stage]), 0);
+          tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tm_a, full0, kb * BK, row_a);
+          tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tm_b, full0, kb * BK, row_b);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = pair_id; u < units; u += num_pairs, ++it) {
+        const int buf = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements = 32 B inside the 128 B swizzle row
+            const uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = make_smem_desc(b_addr + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16<2>(tmem_d, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs once these MMAs have read it
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full[buf], 3);  // accumulator complete, both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs) =====================
+    const int ew = warp - 4;
+    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the only ones this warp may read
+    const int half = ew >> 2;      // column half of the tile
+    constexpr int NCH = BN / 2 / CHUNK;
+    uint8_t* wst = staging + ew * C::WARP_STAGING;
+    uint8_t* Xs = wst;                             // [2][XT]
+    uint8_t* Ys = wst + C::X_BYTES;                // [2][YT]
+    uint8_t* Zs = wst + C::X_BYTES + C::Y_BYTES;   // [2][YT]
+    uint64_t* my_ld = ld_bar + ew * 2;
+    const uint32_t tmem_empty0[2] = {mapa(smem_u32(&tmem_empty[0]), 0), mapa(smem_u32(&tmem_empty[1]), 0)};
+    float alpha = p.alpha;
+    if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
+    const bool res = F32 && p.has_res;
+    const bool loads = res || C::BWD_ACT;
+    const uint32_t ld_bytes = (res ? XT : 0) + (C::BWD_ACT ? YT : 0);
+    const int r = lane;
+    const uint32_t xsw = (uint32_t)(r & 7), ysw = (uint32_t)((r >> 1) & 3);
+    uint32_t g = 0;  // chunks processed so far: staging buffer = g & 1, load-barrier parity = (g >> 1) & 1
+    int it = 0;
+    for (int u = pair_id; u < units; u += num_pairs, ++it) {
+      const int pm = u % p.pair_m_blocks;
+      const int n_blk = u / p.pair_m_blocks;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = pm * (2 * BM) + (int)rank * BM + quarter * 32;
+      const int col0 = n_blk * BN + half * (BN / 2);
+      int nch = 0;
+      if (row0 < p.M && col0 < p.N) {
+        nch = (p.N - col0 + CHUNK - 1) / CHUNK;
+        if (nch > NCH) nch = NCH;
+      }
+      auto issue_load = [&](uint32_t gj, int col) {
+        const uint32_t b = gj & 1;
+        mbar_expect_tx(&my_ld[b], ld_bytes);
+        if (res) tma_load_2d(Xs + b * XT, &tm_r, &my_ld[b], col, row0);
+        if (C::BWD_ACT) tma_load_2d(Zs + b * YT, &tm_z, &my_ld[b], col, row0);
+      };
+      if (loads && lane == 0 && nch > 0) {
+        // side inputs of the first two chunks travel while the MMAs of this tile are still running
+        if (F32) tma_store_wait_read<0>();  // fp32 tiles are updated in place: earlier stores must have drained
+        issue_load(g, col0);
+        if (nch > 1) issue_load(g + 1, col0 + CHUNK);
+      }
+      mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2));
+      if (nch == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty0[buf]);
+        continue;
+      }
+#pragma unroll 1
+      for (int j = 0; j < nch; ++j, ++g) {
+        const uint32_t b = g & 1;
+        const int col = col0 + j * CHUNK;
+        uint32_t rr[32];
+        tmem_ld32(taddr0 + (uint32_t)(j * CHUNK), rr);
+        if (loads) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
+        tmem_ld_wait();
+        if (j == nch - 1) {
+          // last read of this accumulator buffer: hand it back to the MMA issuer before doing the math
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tmem_empty0[buf]);
+        }
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(b4 + i);
+            v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+          }
+        }
+        if (C::BWD_ACT) {
+          const uint8_t* zrow = Zs + b * YT + r * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 a = *reinterpret_cast<const uint4*>(zrow + ((c ^ ysw) << 4));
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = unpack_bf16x2(aw[t]);
+              if (KIND == EPK_GELU_BWD) {
+                v[8 * c + 2 * t] *= gelu_bwd_fast(f.x);
+                v[8 * c + 2 * t + 1] *= gelu_bwd_fast(f.y);
+              } else {
+                v[8 * c + 2 * t] = f.x > 0.0f ? v[8 * c + 2 * t] : 0.0f;
+                v[8 * c + 2 * t + 1] = f.y > 0.0f ? v[8 * c + 2 * t + 1] : 0.0f;
+              }
+            }
+          }
+        }
+        if (alpha != 1.0f) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= alpha;
+        }
+        // staging tiles [b] were last the source of chunk g-2's stores
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        if (C::FWD_ACT) {
+          if (p.has_z) {
+            uint8_t* zrow = Zs + b * YT + r * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              *reinterpret_cast<uint4*>(zrow + ((c ^ ysw) << 4)) =
+                  make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                             pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_fast(v[i]) : fmaxf(v[i], 0.0f);
+        }
+        if (F32) {
+          uint8_t* xrow = Xs + b * XT + r * 128;
+          if (res) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 x = *reinterpret_cast<const float4*>(xrow + ((c ^ xsw) << 4));
+              v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w;
+            }
+          }
+          if (p.has_f32) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              *reinterpret_cast<float4*>(xrow + ((c ^ xsw) << 4)) =
+                  make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          }
+        }
+        if (p.has_out) {
+          uint8_t* yrow = Ys + b * YT + r * 64;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(yrow + ((c ^ ysw) << 4)) =
+                make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                           pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.has_out) tma_store_2d(&tm_y, Ys + b * YT, col, row0);
+          if (C::FWD_ACT && p.has_z) tma_store_2d(&tm_z, Zs + b * YT, col, row0);
+          if (F32 && p.has_f32) tma_store_2d(&tm_x, Xs + b * XT, col, row0);
+          tma_store_commit();
+          if (loads && j + 2 < nch) {
+            if (F32) tma_store_wait_read<0>();  // the in-place tile must be fully read before it is overwritten
+            issue_load(g + 2, col + 2 * CHUNK);
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, (uint32_t)C::TMEM_COLS);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace tc2
+
+// 2-D tensor map over a row-major [outer, inner] matrix (leading dimension ld elements) of bf16 (esize 2) or fp32
+// (esize 4); out-of-range elements read as zero and are not written.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, uint64_t outer, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  tc2::EncodeTiledFn fn = tc2::encode_fn();
+  FV_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  FV_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
+  FV_CHECK((ld * esize) % 16 == 0, "TMA operand row pitch must be a multiple of 16 bytes (ld %llu)",
+           (unsigned long long)ld);
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {ld * (uint64_t)esize};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+namespace tc2 {
+
+template <int BN, int KIND, bool F32>
+static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const Epilogue& e,
+                  cudaStream_t stream) {
+  using C = Cfg<BN, KIND, F32>;
+  CUtensorMap ta, tb, ty, tz, tx, tr;
+  FV_TRY(make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM, 128));
+  FV_TRY(make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN / 2, 128));
+  Params p;
+  p.M = M; p.N = N; p.K = K;
+  p.pair_m_blocks = ceil_div(M, 2 * BM);
+  p.n_blocks = ceil_div(N, BN);
+  p.bias = e.bias; p.alpha_ptr = e.alpha_ptr; p.alpha = e.alpha;
+  const void* zptr = C::FWD_ACT ? e.out_pre : (C::BWD_ACT ? e.aux : nullptr);
+  p.has_out = e.out != nullptr;
+  p.has_z = zptr != nullptr;
+  p.has_f32 = e.out_f32 != nullptr;
+  p.has_res = e.residual != nullptr;
+  ty = ta; tz = ta; tx = ta; tr = ta;  // unused maps stay valid descriptors
+  if (p.has_out) FV_TRY(make_tmap_2d(&ty, e.out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 64));
+  if (p.has_z) FV_TRY(make_tmap_2d(&tz, zptr, 2, (uint64_t)N, (uint64_t)M, (uint64_t)N, CHUNK, 32, 64));
+  if (p.has_f32) FV_TRY(make_tmap_2d(&tx, e.out_f32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
+  if (p.has_res) FV_TRY(make_tmap_2d(&tr, e.residual, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
+  static bool attr_set = false;
+  if (!attr_set) {
+    FV_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, KIND, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int units = p.pair_m_blocks * p.n_blocks;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = units < max_pairs ? units : max_pairs;
+  ProfScope prof(0, 2.0 * M * (double)N * K, stream);
+  gemm_tc2_kernel<BN, KIND, F32><<<2 * pairs, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ty, tz, tx, tr, p);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tc2
+
+// Can the CTA-pair kernel run this problem? (K-major operands, no split-K, plain / activation epilogues.)
+bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind) {
+  (void)M;
+  if (kind != EPK_PLAIN && kind != EPK_GELU && kind != EPK_RELU && kind != EPK_GELU_BWD && kind != EPK_RELU_BWD)
+    return false;
+  const bool f32 = e.out_f32 != nullptr || e.residual != nullptr;
+  if (f32 && kind != EPK_PLAIN) return false;
+  if (e.residual && !e.out_f32) return false;
+  if (N % tc2::CHUNK != 0 || K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) return false;
+  if (e.out && e.ldo % 8 != 0) return false;
+  if (f32 && e.ldo % 4 != 0) return false;
+  auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!al(e.out) || !al(e.out_f32) || !al(e.residual) || !al(e.aux) || !al(e.out_pre) || !al(e.bias)) return false;
+  if ((kind == EPK_GELU_BWD || kind == EPK_RELU_BWD) && e.aux == nullptr) return false;
+  static int v1 = -1;
+  if (v1 < 0) { const char* s = getenv("FERVIT_GEMM_V1"); v1 = (s && atoi(s)) ? 1 : 0; }
+  return v1 == 0;
+}
+
+int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn,
+                  const Epilogue& e, int kind, cudaStream_t stream) {
+  const bool f32 = e.out_f32 != nullptr || e.residual != nullptr;
+  int bn = (force_bn == 128 || force_bn == 256) ? force_bn : (N > 128 ? 256 : 128);
+#define FV_TC2_CASE(BN_, K_, F_) return tc2::launch<BN_, K_, F_>(A, lda, B, ldb, M, N, K, e, stream)
+#define FV_TC2_BN(BN_)                                         \
+  do {                                                         \
+    if (f32) FV_TC2_CASE(BN_, EPK_PLAIN, true);                \
+    switch (kind) {                                            \
+      case EPK_PLAIN: FV_TC2_CASE(BN_, EPK_PLAIN, false);      \
+      case EPK_GELU: FV_TC2_CASE(BN_, EPK_GELU, false);        \
+      case EPK_RELU: FV_TC2_CASE(BN_, EPK_RELU, false);        \
+      case EPK_GELU_BWD: FV_TC2_CASE(BN_, EPK_GELU_BWD, false); \
+      case EPK_RELU_BWD: FV_TC2_CASE(BN_, EPK_RELU_BWD, false); \
+      default: break;                                          \
+    }                                                          \
+  } while (0)
+  if (bn == 256) FV_TC2_BN(256);
+  else FV_TC2_BN(128);
+#undef FV_TC2_BN
+#undef FV_TC2_CASE
+  FV_CHECK(false, "gemm_bf16_tc2: unsupported epilogue kind %d", kind);
+}
+
+}  // namespace fervit

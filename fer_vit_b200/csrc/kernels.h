@@ -8,6 +8,10 @@ namespace fervit {
 int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool b_mn, int M, int N, int K, int splits,
                  int force_bn, const Epilogue& epi, cudaStream_t stream);
 int gemm_bf16_tc_effective_splits(int K, int splits);
+// gemm_tc2.cu (CTA-pair kernel; K-major operands, TMA epilogue)
+bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind);
+int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn, const Epilogue& e,
+                  int kind, cudaStream_t stream);
 // gemm_simt.cu
 int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, int M,
                   int N, int K, int splits, const Epilogue& epi, cudaStream_t stream);

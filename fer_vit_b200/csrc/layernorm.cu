@@ -1,6 +1,8 @@
 // LayerNorm forward / backward over the fp32 residual stream, one warp per token row, fp32 statistics.
 // Replaces ATen native_layer_norm behind timm Block.norm1/norm2 (eps 1e-6, hybrid_latent_vit.py:227-233),
 // nn.TransformerEncoderLayer.norm1/norm2 (eps 1e-5, latent_vit.py:24-31, image_vit.py:101-113).
+// HBM-bound: a row is read once into registers (CH chunks of 128 columns per warp, CH a template parameter so
+// E = 768 keeps 6 float4 per array, not 8), statistics by warp shuffles, every output written once.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -8,10 +10,9 @@ namespace fervit {
 
 namespace ln {
 
-constexpr int MAXCH = 8;  // 8 chunks x 32 lanes x 4 floats = E up to 1024
 constexpr int WARPS = 8;
 
-template <typename AT>
+template <typename AT, int CH>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, int rows, int E, float* __restrict__ out_f32, AT* __restrict__ out_at,
@@ -20,10 +21,10 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
   const float* xr = x + (size_t)row * E;
-  float4 v[MAXCH];
+  float4 v[CH];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < E) {
       v[i] = *reinterpret_cast<const float4*>(xr + c);
@@ -33,7 +34,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   const float mean = warp_sum(s) / (float)E;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < E) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -46,7 +47,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     if (rstd_out) rstd_out[row] = rstd;
   }
 #pragma unroll
-  for (int i = 0; i < MAXCH; ++i) {
+  for (int i = 0; i < CH; ++i) {
     const int c = lane * 4 + i * 128;
     if (c < E) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -64,7 +65,7 @@ ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dres). Optional per-CTA partial sums of
 // dgamma = sum dy*xhat and dbeta = sum dy, reduced afterwards in a fixed order (deterministic).
-template <typename DT, typename AT, bool WGRAD>
+template <typename DT, typename AT, bool WGRAD, int CH>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
@@ -73,20 +74,20 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
   __shared__ float red[WGRAD ? WARPS * 32 * 4 : 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float4 dg[WGRAD ? MAXCH : 1], db[WGRAD ? MAXCH : 1];
+  float4 dg[WGRAD ? CH : 1], db[WGRAD ? CH : 1];
   if (WGRAD) {
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < CH; ++i) {
       dg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       db[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[MAXCH], gd[MAXCH];
+    float4 xh[CH], gd[CH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < CH; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < E) {
         const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)row * E + c);
@@ -105,7 +106,7 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
     s1 = warp_sum(s1) / (float)E;
     s2 = warp_sum(s2) / (float)E;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < CH; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < E) {
         float4 o;
@@ -121,11 +122,11 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
         if (dx_at) {
           if (at_drop.threshold) {
             // the activation-dtype copy feeds the dgrad/wgrad of a sub-layer whose output went through dropout
-            const uint64_t base = (uint64_t)row * E + c;
-            o.x = drop_keep(at_drop.eff(), at_drop.site, base + 0, at_drop.threshold) ? o.x * at_drop.scale : 0.f;
-            o.y = drop_keep(at_drop.eff(), at_drop.site, base + 1, at_drop.threshold) ? o.y * at_drop.scale : 0.f;
-            o.z = drop_keep(at_drop.eff(), at_drop.site, base + 2, at_drop.threshold) ? o.z * at_drop.scale : 0.f;
-            o.w = drop_keep(at_drop.eff(), at_drop.site, base + 3, at_drop.threshold) ? o.w * at_drop.scale : 0.f;
+            const uint64_t base = (uint64_t)row * E + c, seed = at_drop.eff();
+            o.x = drop_keep(seed, at_drop.site, base + 0, at_drop.threshold) ? o.x * at_drop.scale : 0.f;
+            o.y = drop_keep(seed, at_drop.site, base + 1, at_drop.threshold) ? o.y * at_drop.scale : 0.f;
+            o.z = drop_keep(seed, at_drop.site, base + 2, at_drop.threshold) ? o.z * at_drop.scale : 0.f;
+            o.w = drop_keep(seed, at_drop.site, base + 3, at_drop.threshold) ? o.w * at_drop.scale : 0.f;
           }
           store4<AT>(dx_at + (size_t)row * E + c, o);
         }
@@ -137,7 +138,7 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
     float* pg = partial + (size_t)blockIdx.x * 2 * E;
     float* pb = pg + E;
 #pragma unroll
-    for (int i = 0; i < MAXCH; ++i) {
+    for (int i = 0; i < CH; ++i) {
       const int c0 = i * 128;
       if (c0 >= E) break;  // block-uniform
       for (int which = 0; which < 2; ++which) {
@@ -159,18 +160,32 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
   }
 }
 
+static inline int chunks_for(int E) { return (E + 127) / 128; }
+
 }  // namespace ln
+
+#define FV_LN_DISPATCH(CALL)                      \
+  do {                                            \
+    const int ch_ = ln::chunks_for(E);            \
+    if (ch_ <= 2) { CALL(2); }                    \
+    else if (ch_ <= 4) { CALL(4); }               \
+    else if (ch_ <= 6) { CALL(6); }               \
+    else { CALL(8); }                             \
+  } while (0)
 
 template <typename AT>
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, float eps, int rows, int E, float* out_f32,
                   AT* out_at, float* mean, float* rstd, cudaStream_t stream) {
-  FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  FV_CHECK(E % 4 == 0 && E <= 1024, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (rows <= 0) return 0;
   // algorithmic bytes: read x fp32, write each requested output, 8 B of statistics per row
   ProfScope prof(2, (double)rows * E * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0,
                  stream);
-  ln::ln_fwd_kernel<AT><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(x, gamma, beta, eps, rows, E,
-                                                                               out_f32, out_at, mean, rstd);
+#define FV_LN_FWD(CH_)                                                                                          \
+  ln::ln_fwd_kernel<AT, CH_><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(x, gamma, beta, eps, rows, E, \
+                                                                                     out_f32, out_at, mean, rstd)
+  FV_LN_DISPATCH(FV_LN_FWD);
+#undef FV_LN_FWD
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -187,18 +202,24 @@ template <typename DT, typename AT>
 int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
                   const float* dres, int rows, int E, float* dx_f32, AT* dx_at, float* partial, Dropout at_drop,
                   cudaStream_t stream) {
-  FV_CHECK(E % 4 == 0 && E <= ln::MAXCH * 128, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
+  FV_CHECK(E % 4 == 0 && E <= 1024, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (rows <= 0) return 0;
   // algorithmic bytes: read dy and x (and dres), write each requested output, 8 B of statistics per row
   ProfScope prof(2, (double)rows * E * ((double)sizeof(DT) + 4.0 + (dres ? 4.0 : 0.0) + (dx_f32 ? 4.0 : 0.0) +
                                         (dx_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0, stream);
   if (partial) {
     const int grid = layernorm_bwd_grid(rows);
-    ln::ln_bwd_kernel<DT, AT, true><<<grid, ln::WARPS * 32, 0, stream>>>(dy, x, mean, rstd, gamma, dres, rows, E,
-                                                                        dx_f32, dx_at, partial, at_drop);
+#define FV_LN_BWD_W(CH_)                                                                                         \
+  ln::ln_bwd_kernel<DT, AT, true, CH_><<<grid, ln::WARPS * 32, 0, stream>>>(dy, x, mean, rstd, gamma, dres, rows, E, \
+                                                                          dx_f32, dx_at, partial, at_drop)
+    FV_LN_DISPATCH(FV_LN_BWD_W);
+#undef FV_LN_BWD_W
   } else {
-    ln::ln_bwd_kernel<DT, AT, false><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(
-        dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at, nullptr, at_drop);
+#define FV_LN_BWD(CH_)                                                                                    \
+  ln::ln_bwd_kernel<DT, AT, false, CH_><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(        \
+      dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at, nullptr, at_drop)
+    FV_LN_DISPATCH(FV_LN_BWD);
+#undef FV_LN_BWD
   }
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();

@@ -195,10 +195,17 @@ int fervit_premodules_backward(const fervit_premodules* p, const float* x, const
 
 /* y = act(x W^T + b) (+ residual): nn.Linear / F.linear. fp32 mode: x, W fp32; bf16 mode: x, W bf16 ([N,K]).
  * out (act_dtype) and out_f32 may each be NULL; residual fp32 [M,N] may be NULL; pre (act_dtype, pre-activation) may
- * be NULL. force_bn: 0 = auto, else 64/128/256 N tile of the tcgen05 kernel (ignored in fp32 mode). */
+ * be NULL. force_bn (ignored in fp32 mode): 0 = auto; 128 / 256 = N tile of the CTA-pair tcgen05 kernel; -64 / -128 /
+ * -256 = force the single-CTA tcgen05 kernel with that N tile (benchmarks and tests). */
 int fervit_linear_forward(int act_dtype, const void* x, const void* W, const float* bias, const float* residual,
                           int M, int N, int K, int act, void* out, float* out_f32, void* pre, int force_bn,
                           void* stream);
+/* dx[M,K] = (dy[M,N] Wt^T) * act'(aux) (+ residual): the input gradient of nn.Linear fused with the derivative of the
+ * activation that preceded it (autograd of F.linear + nn.GELU / nn.ReLU). Wt is the TRANSPOSED weight [K,N] (act_dtype);
+ * aux (act_dtype, [M,K], pre-activation) is required when act != 0; residual fp32 [M,K] may be NULL; out / out_f32 may
+ * each be NULL. force_bn as above. */
+int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const void* aux, const float* residual, int M,
+                        int N, int K, int act, void* out, float* out_f32, int force_bn, void* stream);
 /* dW[N,K] = alpha * dY^T X  (dY [M,N], X [M,K], act_dtype): the weight gradient of nn.Linear.
  * scratch: fervit_linear_wgrad_scratch_floats(M,N,K) floats. */
 long long fervit_linear_wgrad_scratch_floats(int M, int N, int K);

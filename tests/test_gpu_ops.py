@@ -111,6 +111,70 @@ def test_gemm_bf16_tcgen05(lib, M, N, K, bn):
     assert relerr(out.float(), ref) < 4e-3
 
 
+TC2_SHAPES = [
+    # M, N, K, force_bn  (CTA-pair kernel: N % 32 == 0, K % 8 == 0)
+    (128, 64, 64, 0), (256, 256, 64, 0), (256, 128, 64, 256),         # one pair tile; padded second CTA / N half
+    (300, 192, 136, 0),                                                # odd number of 128-row blocks, K tail
+    (384, 256, 512, 128), (1000, 320, 264, 0),                         # N % BN != 0
+    (4864, 2304, 768, 0), (4864, 768, 768, 0), (4864, 3072, 768, 0), (4864, 768, 3072, 0),   # ViT-B @ B=256
+    (4864, 3072, 768, 128), (4864, 64, 768, 0), (4864, 768, 64, 0),
+    (19 * 7, 768, 768, 0), (9728, 2304, 768, 0),
+]
+
+
+def drelu(x):
+    return (x > 0).double()
+
+
+def dgelu(x):
+    return 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+
+
+@pytest.mark.parametrize("M,N,K,bn", TC2_SHAPES)
+def test_gemm_bf16_tcgen05_pair(lib, M, N, K, bn):
+    """CTA-pair tcgen05 kernel (gemm_tc2.cu): every epilogue family against fp64 math on the same bf16 inputs, and
+    bit-for-bit against the single-CTA kernel where both implement the epilogue."""
+    L = lib
+    g = torch.Generator(device="cuda").manual_seed(M * 5 + N * 11 + K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    acc = x.double() @ W.double().t()
+    errs = {}
+    # (a) bias, bf16 output only
+    out, _, _ = run_linear(L, L.BF16, x, W, b, None, L.ACT_NONE, True, False, False, bn)
+    errs["bias_bf16"] = relerr(out.float(), acc + b)
+    assert errs["bias_bf16"] < 4e-3
+    # (b) bias + fp32 residual -> fp32 and bf16 outputs; fp32 output without residual
+    out, of, _ = run_linear(L, L.BF16, x, W, b, r, L.ACT_NONE, True, True, False, bn)
+    errs["res_f32"] = relerr(of, acc + b + r)
+    assert errs["res_f32"] < 2e-5 and relerr(out.float(), acc + b + r) < 4e-3
+    _, of1, _ = run_linear(L, L.BF16, x, W, b, r, L.ACT_NONE, False, True, False, -256)
+    assert torch.equal(of, of1), "CTA-pair and single-CTA kernels must agree bit for bit (same fp32 accumulation order)"
+    _, of, _ = run_linear(L, L.BF16, x, W, None, None, L.ACT_NONE, False, True, False, bn)
+    errs["plain_f32"] = relerr(of, acc)
+    assert errs["plain_f32"] < 2e-5
+    # (c) forward activation with the pre-activation saved
+    for act, fn in ((L.ACT_GELU, gelu), (L.ACT_RELU, torch.relu)):
+        out, _, pre = run_linear(L, L.BF16, x, W, b, None, act, True, False, True, bn)
+        u = acc + b
+        e_o, e_p = relerr(out.float(), fn(u)), relerr(pre.float(), u)
+        errs[f"act{act}"] = e_o
+        assert e_o < 4e-3 and e_p < 4e-3
+    # (d) input gradient times the activation derivative: GEMM view rows M, columns N, reduction K
+    aux = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    for act, dfn in ((L.ACT_GELU, dgelu), (L.ACT_RELU, drelu)):
+        out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        L.check(L.lib().fervit_linear_dgrad(L.BF16, x.data_ptr(), W.data_ptr(), aux.data_ptr(), None, M, K, N, act,
+                                            out.data_ptr(), None, bn, st()))
+        torch.cuda.synchronize()
+        e = relerr(out.float(), acc * dfn(aux.double()))
+        errs[f"dact{act}"] = e
+        assert e < 4e-3
+    record("gemm_bf16_tcgen05_pair", M=M, N=N, K=K, bn=bn, **errs)
+
+
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K", [(256, 64, 64), (4864, 64, 768), (4864, 768, 64), (608, 1536, 512),
                                    (1000, 128, 208), (4608, 768, 512), (4864, 768, 3072)])

@@ -48,12 +48,26 @@ def time_gemm(M, N, K, bn, iters, act=0, bias=False, residual=False, out_f32=Fal
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--bn", default="0,64,128,256")
+    ap.add_argument("--bn", default="0,128,-256")
     ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--one", default="")
     ap.add_argument("--noflush", action="store_true")
+    ap.add_argument("--sweep", default="", help="M,N,K,bn[;M,N,K,bn...]: time each shape under every isolation flag")
     a = ap.parse_args()
     flush = None if a.noflush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    if a.sweep:
+        # isolation runs (results are garbage, timings only): see Params::debug in csrc/gemm_tc.cu
+        names = {0: "full", 16: "no global stores", 32: "tmem+smem transpose only", 8: "tmem loads only",
+                 4: "no epilogue", 5: "mma only (no tma, no epilogue)", 6: "tma only (no mma, no epilogue)"}
+        for shape in a.sweep.split(";"):
+            M, N, K, bn = [int(v) for v in shape.split(",")]
+            for dbg, nm in names.items():
+                os.environ["FERVIT_GEMM_DEBUG"] = str(dbg)
+                t = time_gemm(M, N, K, bn, a.iters, flush=flush)
+                print(json.dumps({"M": M, "N": N, "K": K, "bn": bn, "debug": dbg, "what": nm, "us": round(t * 1e6, 1),
+                                  "tflops": round(2 * M * N * K / t / 1e12, 1)}), flush=True)
+        os.environ["FERVIT_GEMM_DEBUG"] = "0"
+        return
     if a.one:
         M, N, K, bn = [int(v) for v in a.one.split(",")]
         t = time_gemm(M, N, K, bn, a.iters, flush=flush)
@@ -61,7 +75,7 @@ def main():
         return
     for name, M, N, K in VITB:
         for bn in [int(v) for v in a.bn.split(",")]:
-            if bn > 64 and N <= bn // 2:
+            if abs(bn) > 64 and N <= abs(bn) // 2:
                 continue
             t = time_gemm(M, N, K, bn, a.iters, flush=flush)
             print(json.dumps({"gemm": name, "M": M, "N": N, "K": K, "bn": bn, "us": round(t * 1e6, 1),
