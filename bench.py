@@ -130,6 +130,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--buckets", type=int, default=2)
     ap.add_argument("--profile-only", action="store_true", help="run warm-up + the timed steps and exit (for ncu)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
+                                                            "the captured CUDA graph of the step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
 
@@ -167,7 +169,7 @@ def main():
     model = model.to(dev).train()
     bucketer = parallel.enable_data_parallel(model, num_buckets=args.buckets) if n_gpus > 1 else None
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True)
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True, capturable=not args.no_graph)
 
     # synthetic inputs: a rotating pool larger than the 126 MB L2 (different seed per rank = different shard)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -176,13 +178,17 @@ def main():
     pool_x = torch.randn(n_pool, B, 18, 512, device=dev, generator=g)
     pool_y = torch.randint(0, 7, (n_pool, B), device=dev, generator=g)
 
-    def train_step(x, y):
+    def eager_step(x, y):
         opt.zero_grad(set_to_none=True)
         logits = model(x)
         loss = fv.cross_entropy(logits, y)
         loss.backward()
         opt.step()
         return loss
+
+    # the public train-step API: the whole step captured once as a CUDA graph, replayed per batch
+    graphed = None if args.no_graph else fv.GraphedTrainStep(model, opt, pool_x[0], pool_y[0])
+    train_step = eager_step if graphed is None else graphed
 
     def barrier():
         if n_gpus > 1:
@@ -211,6 +217,8 @@ def main():
     launches0 = L.launch_count()
     ms = timed(lambda i: train_step(pool_x[i % n_pool], pool_y[i % n_pool]), args.steps)
     launches = L.launch_count() - launches0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps
     clocks = sampler.stop() if rank == 0 else {}
     if args.profile_only:
         return
@@ -241,7 +249,7 @@ def main():
         torch.cuda.current_stream().wait_event(ready[k])
         loss = train_step(bufs[k][0], bufs[k][1])
         consumed[k].record()
-        host_loss[i % host_loss.numel()].copy_(loss, non_blocking=True)   # D2H of the step's result
+        host_loss[i % host_loss.numel()].copy_(loss.detach(), non_blocking=True)   # D2H of the step's result
 
     for k in range(2):
         consumed[k].record()
@@ -265,7 +273,7 @@ def main():
         lib.fervit_profile_enable(1)
         psteps = 3
         for i in range(psteps):
-            train_step(pool_x[i % n_pool], pool_y[i % n_pool])
+            eager_step(pool_x[i % n_pool], pool_y[i % n_pool])   # per-kernel events need host launches
         torch.cuda.synchronize()
 
         def read(cls):
@@ -315,7 +323,8 @@ def main():
                              f"({B}/GPU), NCCL all-reduce of 1,605,907 trainable grads in {args.buckets} buckets "
                              "overlapped with backward"),
                 "global_batch": global_batch, "per_gpu_batch": B, "seq_len": 19, "parallelism": f"dp{n_gpus}",
-                "step": "zero_grad + fwd + CE + bwd + fused AdamW over the trainable set",
+                "step": "zero_grad + fwd + CE + bwd + fused AdamW over the trainable set" +
+                        ("" if graphed is None else ", replayed from one captured CUDA graph (fer_vit_b200.GraphedTrainStep)"),
                 "l2": f"inputs rotate over a {n_pool * bytes_per_batch / 1e6:.0f} MB pool (> 126 MB L2); the step's own "
                       "activation working set is > 1.5 GB",
             },

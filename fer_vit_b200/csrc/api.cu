@@ -75,6 +75,11 @@ FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, co
   return gemm_bf16_tc((const bf16*)x, K, false, (const bf16*)W, K, false, M, N, K, 1, force_bn, e, S_(stream));
 }
 
+FV_API int fervit_debug_gemm_clock(double* ns, double* cycles) {
+  FV_CHECK(ns && cycles, "debug_gemm_clock: null argument");
+  return gemm_tc2_clock_probe(ns, cycles);
+}
+
 FV_API int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const void* aux, const float* residual,
                                int M, int N, int K, int act, void* out, float* out_f32, int force_bn, void* stream) {
   FV_CHECK(dy && Wt, "linear_dgrad: null argument");

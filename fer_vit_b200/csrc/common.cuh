@@ -103,6 +103,40 @@ __device__ __forceinline__ float gelu_bwd_fast(float u) {
   gelu_fast_parts(u, cdf, e);
   return fmaf(u * 0.39894228040143267794f, e, cdf);
 }
+// Tensor-core GEMM epilogues (gemm_tc2.cu): MUFU-free polynomials, because at ~23 instructions + 2 MUFU per element
+// the erf form above made the fc1 / fc2-dgrad epilogues slower than the MMAs they hide behind (measured).
+//   Phi(u)   = 0.5 + uc * P8(uc^2),  uc = clamp(u, -4, 4): |error| <= 7e-6 inside, <= 3.2e-5 in the clamped tails
+//   gelu'(u) = 0.5 + uc * Q9(uc^2):                        |error| <= 6e-5 inside, <= 5.4e-4 in the clamped tails
+// (minimax fits of the exact erf forms; bf16 outputs round at 2^-9 = 2e-3 relative).
+__device__ __forceinline__ float gelu_fwd_poly(float u) {
+  const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
+  const float s = uc * uc;
+  float p = 3.463219783e-01f / 4294967296.0f;                    // coefficients of (s/16)^k, k = 8 .. 0
+  p = fmaf(p, s, -1.879982349e+00f / 268435456.0f);
+  p = fmaf(p, s, 4.556960448e+00f / 16777216.0f);
+  p = fmaf(p, s, -6.600791621e+00f / 1048576.0f);
+  p = fmaf(p, s, 6.482043223e+00f / 65536.0f);
+  p = fmaf(p, s, -4.644546053e+00f / 4096.0f);
+  p = fmaf(p, s, 2.528634271e+00f / 256.0f);
+  p = fmaf(p, s, -1.062569537e+00f / 16.0f);
+  p = fmaf(p, s, 3.989227100e-01f);
+  return u * fmaf(uc, p, 0.5f);
+}
+__device__ __forceinline__ float gelu_bwd_poly(float u) {
+  const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
+  const float s = uc * uc;
+  float p = -3.606366035e+00f / 68719476736.0f;                  // (s/16)^k, k = 9 .. 0
+  p = fmaf(p, s, 2.116166659e+01f / 4294967296.0f);
+  p = fmaf(p, s, -5.557563405e+01f / 268435456.0f);
+  p = fmaf(p, s, 8.697387332e+01f / 16777216.0f);
+  p = fmaf(p, s, -9.125917374e+01f / 1048576.0f);
+  p = fmaf(p, s, 6.839210087e+01f / 65536.0f);
+  p = fmaf(p, s, -3.771883499e+01f / 4096.0f);
+  p = fmaf(p, s, 1.521041010e+01f / 256.0f);
+  p = fmaf(p, s, -4.250744890e+00f / 16.0f);
+  p = fmaf(p, s, 7.978260665e-01f);
+  return fmaf(uc, p, 0.5f);
+}
 __device__ __forceinline__ float act_fwd(int act, float x) {
   if (act == ACT_RELU) return fmaxf(x, 0.0f);
   if (act == ACT_GELU) return gelu_fwd(x);

@@ -16,11 +16,51 @@ __global__ void cast_kernel(const float* __restrict__ src, AT* __restrict__ dst,
   }
 }
 
+constexpr int WC_BATCH = 32;
+
 // ---- fp32 [R,C] -> bf16 [R,C] and/or bf16 [C,R] (weight caches: W for forward, W^T for dgrad) ----
 __global__ void weight_cache_kernel(const float* __restrict__ src, int R, int C, bf16* __restrict__ dst,
                                     bf16* __restrict__ dst_t) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = src[(size_t)r * C + c];
+      if (dst) dst[(size_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dst_t) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < R && c < C) dst_t[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// ---- the same for up to WC_BATCH matrices in one launch (the trainable weights are re-cast every step) ----
+struct WcBatch {
+  const float* src[WC_BATCH];
+  bf16* dst[WC_BATCH];
+  bf16* dst_t[WC_BATCH];
+  int R[WC_BATCH], C[WC_BATCH];
+  int tile0[WC_BATCH + 1];  // first 32x32 tile of each matrix in the flat grid
+  int n;
+};
+__global__ void weight_cache_batch_kernel(const __grid_constant__ WcBatch b) {
+  __shared__ float tile[32][33];
+  int m = 0;
+  while (m + 1 < b.n && (int)blockIdx.x >= b.tile0[m + 1]) ++m;
+  const int R = b.R[m], C = b.C[m];
+  const int t = blockIdx.x - b.tile0[m];
+  const int tiles_c = (C + 31) / 32;
+  const int c0 = (t % tiles_c) * 32, r0 = (t / tiles_c) * 32;
+  const float* __restrict__ src = b.src[m];
+  bf16* __restrict__ dst = b.dst[m];
+  bf16* __restrict__ dst_t = b.dst_t[m];
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
     float v = 0.f;
@@ -280,6 +320,28 @@ int weight_cache(const float* src, int R, int C, bf16* dst, bf16* dst_t, cudaStr
   ew::weight_cache_kernel<<<grid, block, 0, stream>>>(src, R, C, dst, dst_t);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int weight_cache_batch(const float* const* src, const int* R, const int* C, bf16* const* dst, bf16* const* dst_t, int n,
+                       cudaStream_t stream) {
+  for (int base = 0; base < n; base += ew::WC_BATCH) {
+    ew::WcBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n = (n - base < ew::WC_BATCH) ? n - base : ew::WC_BATCH;
+    int tiles = 0;
+    for (int i = 0; i < b.n; ++i) {
+      b.src[i] = src[base + i]; b.dst[i] = dst[base + i]; b.dst_t[i] = dst_t[base + i];
+      b.R[i] = R[base + i]; b.C[i] = C[base + i];
+      b.tile0[i] = tiles;
+      tiles += ceil_div(R[base + i], 32) * ceil_div(C[base + i], 32);
+    }
+    b.tile0[b.n] = tiles;
+    if (tiles == 0) continue;
+    ew::weight_cache_batch_kernel<<<tiles, dim3(32, 8), 0, stream>>>(b);
+    FV_COUNT_LAUNCH();
+    FV_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -72,7 +72,11 @@ struct Params {
   const float* alpha_ptr;
   float alpha;
   int has_out, has_z, has_f32, has_res;
+  int debug;  // timing experiments only (results are garbage): 1 no TMA loads, 2 no MMAs, 4 no epilogue, 8 record clocks
 };
+
+// [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
+__device__ unsigned long long g_clock_probe[4];
 
 template <int BN, int KIND, bool F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -102,6 +106,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int units = p.pair_m_blocks * p.n_blocks;
   const int total_kb = (p.K + BK - 1) / BK;
 
+  if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_clock_probe[0] = t;
+    g_clock_probe[2] = (unsigned long long)clock64();
+  }
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a);
     prefetch_tmap(&tm_b);
@@ -133,7 +143,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    if (lane == 0 && (p.debug & 3) != 3) {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = pair_id; u < units; u += num_pairs) {
@@ -143,6 +153,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int row_b = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait_cluster(&empty_bar[stage], phase ^ 1, 1);
+          if (p.debug & 1) {
+            if (leader) mbar_arrive(&full_bar[stage]);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
           const uint32_t full0 = mapa(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tm_a, full0, kb * BK, row_a);
@@ -164,9 +179,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         mbar_wait_cluster(&tmem_empty[buf], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-        for (int kb = 0; kb < total_kb; ++kb) {
+        for (int kb = 0; kb < ((p.debug & 3) == 3 ? 0 : total_kb); ++kb) {
           mbar_wait_cluster(&full_bar[stage], phase, 3);
           tc_fence_after();
+          if (p.debug & 2) {
+            mbar_arrive(&empty_bar[stage]);
+            mbar_arrive_cluster(mapa(smem_u32(&empty_bar[stage]), 1));
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t a_addr = smem_u32(smem_a + stage * C::A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * C::B_BYTES);
 #pragma unroll
@@ -179,7 +200,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_pair(&tmem_full[buf], 3);  // accumulator complete, both CTAs
+        if (p.debug & 2) {
+          mbar_arrive(&tmem_full[buf]);
+          mbar_arrive_cluster(mapa(smem_u32(&tmem_full[buf]), 1));
+        } else {
+          umma_commit_pair(&tmem_full[buf], 3);  // accumulator complete, both CTAs
+        }
       }
     }
   } else if (warp >= 4) {
@@ -215,6 +241,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         nch = (p.N - col0 + CHUNK - 1) / CHUNK;
         if (nch > NCH) nch = NCH;
       }
+      if (p.debug & 4) nch = 0;
       auto issue_load = [&](uint32_t gj, int col) {
         const uint32_t b = gj & 1;
         mbar_expect_tx(&my_ld[b], ld_bytes);
@@ -236,23 +263,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         if (lane == 0) mbar_arrive_cluster(tmem_empty0[buf]);
         continue;
       }
+      uint32_t rr[32];
+      tmem_ld32(taddr0, rr);
 #pragma unroll 1
       for (int j = 0; j < nch; ++j, ++g) {
         const uint32_t b = g & 1;
         const int col = col0 + j * CHUNK;
-        uint32_t rr[32];
-        tmem_ld32(taddr0 + (uint32_t)(j * CHUNK), rr);
         if (loads) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
         tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          asm volatile("" : "+r"(rr[i]));  // pin every use of the loaded registers after the wait
+          v[i] = __uint_as_float(rr[i]);
+        }
+        // the next chunk's accumulators travel TMEM -> registers while this chunk is processed
+        if (j + 1 < nch) tmem_ld32(taddr0 + (uint32_t)((j + 1) * CHUNK), rr);
         if (j == nch - 1) {
           // last read of this accumulator buffer: hand it back to the MMA issuer before doing the math
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tmem_empty0[buf]);
         }
-        float v[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rr[i]);
         if (p.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
@@ -271,8 +303,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int t = 0; t < 4; ++t) {
               const float2 f = unpack_bf16x2(aw[t]);
               if (KIND == EPK_GELU_BWD) {
-                v[8 * c + 2 * t] *= gelu_bwd_fast(f.x);
-                v[8 * c + 2 * t + 1] *= gelu_bwd_fast(f.y);
+                v[8 * c + 2 * t] *= gelu_bwd_poly(f.x);
+                v[8 * c + 2 * t + 1] *= gelu_bwd_poly(f.y);
               } else {
                 v[8 * c + 2 * t] = f.x > 0.0f ? v[8 * c + 2 * t] : 0.0f;
                 v[8 * c + 2 * t + 1] = f.y > 0.0f ? v[8 * c + 2 * t + 1] : 0.0f;
@@ -285,7 +317,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           for (int i = 0; i < 32; ++i) v[i] *= alpha;
         }
         // staging tiles [b] were last the source of chunk g-2's stores
-        if (lane == 0) tma_store_wait_read<1>();
+        if (lane == 0 && !(p.debug & (16 | 64))) tma_store_wait_read<1>();
         __syncwarp();
         if (C::FWD_ACT) {
           if (p.has_z) {
@@ -297,7 +329,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                              pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
           }
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_fast(v[i]) : fmaxf(v[i], 0.0f);
+          for (int i = 0; i < 32; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_poly(v[i]) : fmaxf(v[i], 0.0f);
         }
         if (F32) {
           uint8_t* xrow = Xs + b * XT + r * 128;
@@ -323,9 +355,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                 make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
                            pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
         }
-        fence_proxy_async_smem();
+        if (!(p.debug & 32)) fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && !(p.debug & 16)) {
           if (p.has_out) tma_store_2d(&tm_y, Ys + b * YT, col, row0);
           if (C::FWD_ACT && p.has_z) tma_store_2d(&tm_z, Zs + b * YT, col, row0);
           if (F32 && p.has_f32) tma_store_2d(&tm_x, Xs + b * XT, col, row0);
@@ -344,6 +376,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   cluster_sync();
   tc_fence_after();
   if (warp == 2) tmem_dealloc<2>(tmem_base, (uint32_t)C::TMEM_COLS);
+  if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_clock_probe[1] = t;
+    g_clock_probe[3] = (unsigned long long)clock64();
+  }
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -411,6 +449,11 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   p.has_z = zptr != nullptr;
   p.has_f32 = e.out_f32 != nullptr;
   p.has_res = e.residual != nullptr;
+  {
+    static int dbg = -1;
+    if (dbg != 0) { const char* s = getenv("FERVIT_GEMM_DEBUG"); dbg = s ? (atoi(s) | (1 << 30)) : 0; }
+    p.debug = dbg & ~(1 << 30);
+  }
   ty = ta; tz = ta; tx = ta; tr = ta;  // unused maps stay valid descriptors
   if (p.has_out) FV_TRY(make_tmap_2d(&ty, e.out, 2, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 64));
   if (p.has_z) FV_TRY(make_tmap_2d(&tz, zptr, 2, (uint64_t)N, (uint64_t)M, (uint64_t)N, CHUNK, 32, 64));
@@ -433,6 +476,15 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
 }
 
 }  // namespace tc2
+
+// diagnostics (FERVIT_GEMM_DEBUG bit 8): wall nanoseconds and SM cycles of CTA 0 of the last CTA-pair GEMM
+int gemm_tc2_clock_probe(double* ns, double* cycles) {
+  unsigned long long h[4];
+  FV_CUDA(cudaMemcpyFromSymbol(h, tc2::g_clock_probe, sizeof(h)));
+  *ns = (double)(h[1] - h[0]);
+  *cycles = (double)(h[3] - h[2]);
+  return 0;
+}
 
 // Can the CTA-pair kernel run this problem? (K-major operands, no split-K, plain / activation epilogues.)
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind) {

@@ -12,6 +12,7 @@ int gemm_bf16_tc_effective_splits(int K, int splits);
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind);
 int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn, const Epilogue& e,
                   int kind, cudaStream_t stream);
+int gemm_tc2_clock_probe(double* ns, double* cycles);
 // gemm_simt.cu
 int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, int M,
                   int N, int K, int splits, const Epilogue& epi, cudaStream_t stream);
@@ -30,6 +31,8 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
 // elementwise.cu
 template <typename AT> int cast_to_act(const float* src, AT* dst, size_t n, cudaStream_t stream);
 int weight_cache(const float* src, int R, int C, bf16* dst, bf16* dst_t, cudaStream_t stream);
+int weight_cache_batch(const float* const* src, const int* R, const int* C, bf16* const* dst, bf16* const* dst_t, int n,
+                       cudaStream_t stream);
 template <typename AT> int im2col(const float* x, AT* out, int B, int C, int H, int W, int P, cudaStream_t stream);
 template <typename AT>
 int cls_rows(const float* cls, const float* pos, float* x0, AT* x0_at, int B, int S, int E, Dropout drop,

@@ -84,12 +84,14 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
   }
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     const float mu = mean[row], rs = rstd[row];
-    float4 xh[CH], gd[CH];
+    float4 xh[CH], gd[CH], rsd[CH];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
       const int c = lane * 4 + i * 128;
       if (c < E) {
+        // the residual gradient is fetched up front with the other operands: one memory round trip per row, not two
+        if (dres) rsd[i] = *reinterpret_cast<const float4*>(dres + (size_t)row * E + c);
         const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)row * E + c);
         const float4 d = load4<DT>(dy + (size_t)row * E + c);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -114,10 +116,7 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
         o.y = rs * (gd[i].y - s1 - xh[i].y * s2);
         o.z = rs * (gd[i].z - s1 - xh[i].z * s2);
         o.w = rs * (gd[i].w - s1 - xh[i].w * s2);
-        if (dres) {
-          const float4 r = *reinterpret_cast<const float4*>(dres + (size_t)row * E + c);
-          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-        }
+        if (dres) { o.x += rsd[i].x; o.y += rsd[i].y; o.z += rsd[i].z; o.w += rsd[i].w; }
         if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + (size_t)row * E + c) = o;
         if (dx_at) {
           if (at_drop.threshold) {

@@ -760,21 +760,32 @@ FV_API int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n
   if (plan->cfg.mode != FERVIT_BF16) return 0;
   FV_CHECK(plan->wcache != nullptr, "refresh_wcache: no cache buffer set");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  auto one = [&](int s) -> int {
+  // every requested matrix goes into batched launches (32 matrices each): the trainable weights are re-cast on every
+  // step, and one launch per matrix would cost more than the casts themselves
+  std::vector<const float*> src;
+  std::vector<bf16*> dst, dst_t;
+  std::vector<int> Rs, Cs;
+  auto add = [&](int s) -> int {
     int R, C;
     if (!weight_shape(plan, s, &R, &C)) return 0;
     FV_CHECK(plan->params[s] != nullptr, "refresh_wcache: parameter slot %d not set", s);
-    return weight_cache(plan->P(s), R, C, const_cast<bf16*>(plan->WB(s)), const_cast<bf16*>(plan->WBT(s)), st);
+    src.push_back(plan->P(s));
+    dst.push_back(const_cast<bf16*>(plan->WB(s)));
+    dst_t.push_back(const_cast<bf16*>(plan->WBT(s)));
+    Rs.push_back(R);
+    Cs.push_back(C);
+    return 0;
   };
   if (slots == nullptr) {
-    for (int s = 0; s < plan->nslots(); ++s) FV_TRY(one(s));
+    for (int s = 0; s < plan->nslots(); ++s) FV_TRY(add(s));
   } else {
     for (int i = 0; i < n; ++i) {
       FV_CHECK(slots[i] >= 0 && slots[i] < plan->nslots(), "refresh_wcache: bad slot %d", slots[i]);
-      FV_TRY(one(slots[i]));
+      FV_TRY(add(slots[i]));
     }
   }
-  return 0;
+  if (src.empty()) return 0;
+  return weight_cache_batch(src.data(), Rs.data(), Cs.data(), dst.data(), dst_t.data(), (int)src.size(), st);
 }
 
 FV_API long long fervit_plan_workspace_bytes(const fervit_plan* plan, int B, int save_for_backward) {

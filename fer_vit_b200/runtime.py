@@ -102,7 +102,11 @@ class PlanRunner:
                 if t is None:
                     continue
                 st = (t.data_ptr(), t._version)
-                if self._wstate.get(s) != st:
+                # frozen weights: re-cast when (data_ptr, version) moved (load_state_dict, manual edits). Trainable
+                # weights: re-cast on EVERY call — fused optimizers (torch.optim.AdamW(fused=True)) update parameters
+                # without bumping the version counter, and under CUDA-graph capture the host sees no update at all,
+                # so the cast has to be part of the step itself (one batched kernel launch, see plan.cu).
+                if self._wstate.get(s) != st or t.requires_grad:
                     stale.append(s)
                     self._wstate[s] = st
             if stale:

@@ -237,6 +237,10 @@ int fervit_dropout_mask(float* out, long long n, float p, unsigned long long see
 #define FERVIT_SITE_INPUT 0xFFFF0u
 #define FERVIT_SITE_HEAD 0xFFFF1u
 
+/* Diagnostics: with FERVIT_GEMM_DEBUG bit 8 set, the CTA-pair GEMM records the wall time (ns, %globaltimer) and the SM
+ * cycle count (clock64) of its CTA 0; cycles / ns = the SM clock in GHz while the kernel ran. */
+int fervit_debug_gemm_clock(double* ns, double* cycles);
+
 /* fp32 -> bf16 cast (n multiple of 4) */
 int fervit_cast_bf16(const float* src, void* dst, long long n, void* stream);
 

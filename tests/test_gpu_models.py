@@ -355,3 +355,67 @@ def test_inference_and_checkpoint_roundtrip(tmp_path):
         again.input_proj.weight.mul_(2.0)
         d = again(x)
     assert relerr(c, a) < 2e-2 and relerr(d, c) > 1e-3
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager():
+    """fer_vit_b200.GraphedTrainStep replays exactly the kernels of the eager step: after the same three AdamW steps on
+    the same batches, two models that started identical hold bit-identical parameters and losses. Dropout off (eval-mode
+    head) so both draw no masks; the optimizer updates make the trainable bf16 weight re-casts part of the graph."""
+    import copy
+    import fer_vit_b200 as fv
+    g = load_golden("hybrid_adapter")
+    torch.manual_seed(0)
+    m1 = build_model("hybrid_adapter", "bf16")
+    m1.load_state_dict(g["sd"], strict=True)
+    m1 = m1.cuda().eval()
+    m2 = copy.deepcopy(m1)
+    xs = [torch.randn_like(g["x"]).cuda() for _ in range(3)]
+    ys = [torch.randint(0, 7, g["y"].shape).cuda() for _ in range(3)]
+
+    def make_opt(m):
+        return torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-2, fused=True, capturable=True)
+    o1, o2 = make_opt(m1), make_opt(m2)
+    # the graphed step warms up on its example batch (3 eager steps): give the eager twin the same history
+    stepper = fv.GraphedTrainStep(m2, o2, xs[0], ys[0], warmup=3)
+    losses1, losses2 = [], []
+    for _ in range(3):  # the 3 warm-up steps on (xs[0], ys[0]); the capture pass records kernels without running them
+        o1.zero_grad(set_to_none=True)
+        fv.cross_entropy(m1(xs[0]), ys[0]).backward()
+        o1.step()
+    for x, y in zip(xs, ys):
+        o1.zero_grad(set_to_none=True)
+        l1 = fv.cross_entropy(m1(x), y)
+        l1.backward()
+        o1.step()
+        losses1.append(float(l1))
+        losses2.append(float(stepper(x, y)))
+    torch.cuda.synchronize()
+    assert stepper.launches_per_replay > 50
+    assert losses1 == losses2, (losses1, losses2)
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), k
+
+
+@pytest.mark.gpu
+def test_fused_optimizer_updates_reach_the_bf16_weight_cache():
+    """torch.optim.AdamW(fused=True) mutates parameters without bumping Tensor._version, so the derived bf16 weight
+    cache cannot rely on version counters for trainable weights: after a fused step the model must compute with the
+    NEW weights — its logits equal those of a fresh copy (fresh cache) built from its state_dict."""
+    import copy
+    g = load_golden("hybrid_adapter")
+    m = build_model("hybrid_adapter", "bf16")
+    m.load_state_dict(g["sd"], strict=True)
+    m = m.cuda().eval()
+    x, y = g["x"].cuda(), g["y"].cuda()
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=5e-2, fused=True)
+    before = m(x).detach().clone()
+    for _ in range(2):
+        opt.zero_grad(set_to_none=True)
+        fv_loss = __import__("fer_vit_b200").cross_entropy(m(x), y)
+        fv_loss.backward()
+        opt.step()
+    after = m(x).detach()
+    fresh = copy.deepcopy(m)
+    assert torch.equal(after, fresh(x).detach()), "stale bf16 weight cache after a fused optimizer step"
+    assert relerr(after, before) > 1e-3, "the optimizer steps should have moved the logits"

@@ -52,20 +52,35 @@ def main():
     ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--one", default="")
     ap.add_argument("--noflush", action="store_true")
+    ap.add_argument("--epi-sweep", action="store_true")
+    ap.add_argument("--kinds", default="plain", help="epilogue families for --sweep: plain,bias,gelu,res_f32")
     ap.add_argument("--sweep", default="", help="M,N,K,bn[;M,N,K,bn...]: time each shape under every isolation flag")
     a = ap.parse_args()
     flush = None if a.noflush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     if a.sweep:
-        # isolation runs (results are garbage, timings only): see Params::debug in csrc/gemm_tc.cu
-        names = {0: "full", 16: "no global stores", 32: "tmem+smem transpose only", 8: "tmem loads only",
-                 4: "no epilogue", 5: "mma only (no tma, no epilogue)", 6: "tma only (no mma, no epilogue)"}
+        # isolation runs (results are garbage, timings only): see Params::debug in csrc/gemm_tc2.cu (bn >= 0, CTA-pair
+        # kernel) and csrc/gemm_tc.cu (bn < 0, single-CTA kernel). kw selects the epilogue family.
+        import ctypes
+        names = {0: "full", 4: "no epilogue", 5: "mma only", 6: "tma only", 3: "epilogue only"}
+        if a.epi_sweep:
+            names = {3: "epilogue only", 3 | 16: "epi: no tma stores", 3 | 16 | 32: "epi: no stores, no proxy fence",
+                     3 | 64: "epi: stores without wait_group.read", 64: "full without wait_group.read"}
+        kws = {"plain": {}, "bias": dict(bias=True), "gelu": dict(act=2, bias=True),
+               "res_f32": dict(bias=True, residual=True, out_f32=True)}
         for shape in a.sweep.split(";"):
             M, N, K, bn = [int(v) for v in shape.split(",")]
-            for dbg, nm in names.items():
-                os.environ["FERVIT_GEMM_DEBUG"] = str(dbg)
-                t = time_gemm(M, N, K, bn, a.iters, flush=flush)
-                print(json.dumps({"M": M, "N": N, "K": K, "bn": bn, "debug": dbg, "what": nm, "us": round(t * 1e6, 1),
-                                  "tflops": round(2 * M * N * K / t / 1e12, 1)}), flush=True)
+            for kname in a.kinds.split(","):
+                for dbg, nm in names.items():
+                    os.environ["FERVIT_GEMM_DEBUG"] = str(dbg | 8)
+                    t = time_gemm(M, N, K, bn, a.iters, flush=flush, **kws[kname])
+                    ns, cyc = ctypes.c_double(), ctypes.c_double()
+                    ghz = None
+                    if bn >= 0:
+                        L.check(L.lib().fervit_debug_gemm_clock(ctypes.byref(ns), ctypes.byref(cyc)))
+                        ghz = round(cyc.value / max(ns.value, 1.0), 3)
+                    print(json.dumps({"M": M, "N": N, "K": K, "bn": bn, "epi": kname, "debug": dbg, "what": nm,
+                                      "us": round(t * 1e6, 1), "tflops": round(2 * M * N * K / t / 1e12, 1),
+                                      "kernel_us_cta0": round(ns.value / 1e3, 1), "sm_ghz": ghz}), flush=True)
         os.environ["FERVIT_GEMM_DEBUG"] = "0"
         return
     if a.one:
