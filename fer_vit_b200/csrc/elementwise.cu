@@ -283,6 +283,77 @@ __global__ void adapter_finalize_kernel(const float* __restrict__ part, int npar
   }
 }
 
+// ---- deferred gradient finalisation of the AdapterModules (hybrid_latent_vit.py:249-265) ----
+// During a block's backward only PARTIAL sums are produced (split-K slabs of the two weight-gradient GEMMs, per-chunk
+// column sums of dy and du). Once per backward stage group, two launches finish every block of the group:
+//   dW2 = alpha * sum_s w2_part[s]          dW1 = sum_s w1_part[s]
+//   db2 = alpha * colsum(dy)                db1 = colsum(du)
+//   dalpha = <W2, sum_s w2_part[s]> + b2 . colsum(dy)
+// (dalpha = sum dy * (W2 g + b2); sum_t dy_t^T W2 g_t = <W2, dy^T g>, so no [T, A] intermediate is needed.)
+// All sums run in a fixed order: deterministic, no atomics.
+struct AdFinBatch {
+  AdapterGradJob job[AD_FIN_MAX];
+  int n;
+};
+constexpr int AD_FIN_CTAS = 24;  // CTAs per job in phase 1; the last one also does the bias / column-sum part
+
+__global__ void __launch_bounds__(256)
+adapter_grad_phase1_kernel(const __grid_constant__ AdFinBatch b, float* __restrict__ dalpha_part) {
+  __shared__ float red[8];
+  const AdapterGradJob& j = b.job[blockIdx.y];
+  const float alpha = __ldg(j.alpha_ptr);
+  const int n4 = j.E * j.A / 4;
+  float dot = 0.f;
+  // dW2 [E, A] and dW1 [A, E]: same element count
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a2;
+#pragma unroll 4
+    for (int s = 0; s < j.s2; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(j.w2_part + ((size_t)s * n4 + i) * 4);
+      a2.x += v.x; a2.y += v.y; a2.z += v.z; a2.w += v.w;
+    }
+#pragma unroll 4
+    for (int s = 0; s < j.s1; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(j.w1_part + ((size_t)s * n4 + i) * 4);
+      a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+    }
+    const float4 w = __ldg(reinterpret_cast<const float4*>(j.W2) + i);
+    dot += (w.x * a2.x + w.y * a2.y) + (w.z * a2.z + w.w * a2.w);
+    *reinterpret_cast<float4*>(j.dW2 + (size_t)i * 4) = make_float4(alpha * a2.x, alpha * a2.y, alpha * a2.z, alpha * a2.w);
+    *reinterpret_cast<float4*>(j.dW1 + (size_t)i * 4) = a1;
+  }
+  if (blockIdx.x == gridDim.x - 1) {
+    // column sums: db2 = alpha * colsum(dy) [E], db1 = colsum(du) [A]; dalpha += b2 . colsum(dy)
+    for (int c = threadIdx.x; c < j.E; c += blockDim.x) {
+      float cs = 0.f;
+      for (int k = 0; k < j.chunks; ++k) cs += j.cs_dy[(size_t)k * j.E + c];
+      dot += __ldg(j.b2 + c) * cs;
+      j.db2[c] = alpha * cs;
+    }
+    for (int c = threadIdx.x; c < j.A; c += blockDim.x) {
+      float cs = 0.f;
+      for (int k = 0; k < j.chunks; ++k) cs += j.cs_du[(size_t)k * j.A + c];
+      j.db1[c] = cs;
+    }
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    dalpha_part[blockIdx.y * gridDim.x + blockIdx.x] = t;
+  }
+}
+__global__ void adapter_grad_phase2_kernel(const __grid_constant__ AdFinBatch b, const float* __restrict__ dalpha_part,
+                                           int parts) {
+  const int jb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (jb >= b.n) return;
+  float t = 0.f;
+  for (int i = 0; i < parts; ++i) t += dalpha_part[jb * parts + i];
+  b.job[jb].dalpha[0] = t;
+}
+
 __global__ void dropout_mask_kernel(float* __restrict__ out, size_t n, Dropout drop) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     out[i] = drop_keep(drop.eff(), drop.site, i, drop.threshold) ? drop.scale : 0.f;
@@ -433,6 +504,42 @@ int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha
   ew::splitk_reduce_kernel<<<ew::grid_for(n / 4, 64), 64, 0, stream>>>(partial, splits, n / 4, alpha_ptr, alpha, out);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
+  return 0;
+}
+
+// per-chunk column sums only: scratch [colsum_chunks(R)][C]; reduced later (adapter_grad_finalize)
+template <typename T>
+int colsum_partial(const T* in, int R, int C, long long ld, float* scratch, cudaStream_t stream) {
+  FV_CHECK(C % 4 == 0 && ld % 4 == 0, "colsum_partial: column count and leading dimension must be multiples of 4");
+  const int chunks = colsum_chunks(R);
+  const int rpc = ceil_div(R, chunks);
+  dim3 grid(ceil_div(C, 128), chunks), block(32, 8);
+  ew::colsum_partial_kernel<T><<<grid, block, 0, stream>>>(in, R, C, ld, rpc, scratch, make_dropout(0.f, 0, 0));
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int colsum_partial<float>(const float*, int, int, long long, float*, cudaStream_t);
+template int colsum_partial<bf16>(const bf16*, int, int, long long, float*, cudaStream_t);
+
+int adapter_grad_finalize_scratch_floats() { return AD_FIN_MAX * ew::AD_FIN_CTAS; }
+
+// jobs: one per AdapterModule whose gradients are due; scratch: adapter_grad_finalize_scratch_floats() floats
+int adapter_grad_finalize(const AdapterGradJob* jobs, int n, float* scratch, cudaStream_t stream) {
+  for (int base = 0; base < n; base += AD_FIN_MAX) {
+    ew::AdFinBatch b;
+    memset(&b, 0, sizeof(b));
+    b.n = (n - base < AD_FIN_MAX) ? n - base : AD_FIN_MAX;
+    for (int i = 0; i < b.n; ++i) {
+      b.job[i] = jobs[base + i];
+      FV_CHECK((b.job[i].E * b.job[i].A) % 4 == 0, "adapter_grad_finalize: E * A must be a multiple of 4");
+    }
+    ew::adapter_grad_phase1_kernel<<<dim3(ew::AD_FIN_CTAS, b.n), 256, 0, stream>>>(b, scratch);
+    FV_COUNT_LAUNCH();
+    ew::adapter_grad_phase2_kernel<<<1, 32, 0, stream>>>(b, scratch, ew::AD_FIN_CTAS);
+    FV_COUNT_LAUNCH();
+    FV_LAUNCH_CHECK();
+  }
   return 0;
 }
 

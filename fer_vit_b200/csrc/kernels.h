@@ -48,6 +48,23 @@ int colsum(const T* in, int R, int C, long long ld, float* scratch, const float*
 int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream);
 int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
                   cudaStream_t stream);
+template <typename T>
+int colsum_partial(const T* in, int R, int C, long long ld, float* scratch, cudaStream_t stream);
+// deferred AdapterModule gradient finalisation (see elementwise.cu)
+constexpr int AD_FIN_MAX = 16;
+struct AdapterGradJob {
+  const float* w2_part;  // [s2][E*A] split-K slabs of dy^T g
+  const float* w1_part;  // [s1][A*E] split-K slabs of du^T x
+  const float* cs_dy;    // [chunks][E] per-chunk column sums of dy
+  const float* cs_du;    // [chunks][A] per-chunk column sums of du
+  const float* W2;       // [E, A] fp32 parameter (adapter.2.weight)
+  const float* b2;       // [E]
+  const float* alpha_ptr;
+  float *dW2, *dW1, *db2, *db1, *dalpha;
+  int s2, s1, chunks, E, A;
+};
+int adapter_grad_finalize_scratch_floats();
+int adapter_grad_finalize(const AdapterGradJob* jobs, int n, float* scratch, cudaStream_t stream);
 int adapter_bwd_parts(size_t n);
 template <typename AT>
 int adapter_bwd_glue(const float* p, const AT* u, const AT* g, const float* alpha_ptr, size_t n, AT* du, float* part,

@@ -59,12 +59,13 @@ struct Bufs {
   void* d_big;                 // [T, max(3E,F)] act
   void* d_e1;                  // [T,E] act
   void* d_e2;                  // [T,E] act
-  float* p_ad;                 // [T,A] fp32
   void* du_ad;                 // [T,A] act
   void* dtok;                  // [B*L,E] act
   void* dain;                  // [B*L,Din] act
-  float* ad_part;
-  float* ad_cs;                // [E]
+  // per-block partial sums of the AdapterModule gradients, finished once per backward stage group
+  struct AdParts { float *w2_part, *w1_part, *cs_dy, *cs_du; int s2, s1, chunks; };
+  std::vector<AdParts> ad;
+  float* ad_fin;               // scratch of adapter_grad_finalize
   float* scratch;
   size_t scratch_floats;
 };
@@ -251,10 +252,19 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
     b.d_e1 = ar.take<AT>(T * E);
     b.d_e2 = ar.take<AT>(T * E);
     if (A) {
-      b.p_ad = ar.take<float>(T * A);
       b.du_ad = ar.take<AT>(T * A);
-      b.ad_part = ar.take<float>((size_t)adapter_bwd_parts(T * A));
-      b.ad_cs = ar.take<float>(E);
+      b.ad.resize(c.depth);
+      for (int i = 0; i < c.depth; ++i) {
+        Bufs::AdParts& q = b.ad[i];
+        q.s2 = wgrad_splits(bf, (int)E, (int)A, (int)T);
+        q.s1 = wgrad_splits(bf, (int)A, (int)E, (int)T);
+        q.chunks = colsum_chunks((int)T);
+        q.w2_part = ar.take<float>((size_t)q.s2 * E * A);
+        q.w1_part = ar.take<float>((size_t)q.s1 * A * E);
+        q.cs_dy = ar.take<float>((size_t)q.chunks * E);
+        q.cs_du = ar.take<float>((size_t)q.chunks * A);
+      }
+      b.ad_fin = ar.take<float>((size_t)adapter_grad_finalize_scratch_floats());
     }
     b.dtok = ar.take<AT>(Tl * E);
     b.dain = p->has_pre ? (void*)ar.take<AT>(Tl * c.Din) : nullptr;
@@ -312,6 +322,19 @@ int wgrad(const Ctx& c, const AT* dY, int Nout, const AT* X, int Kin, int T, con
   }
   if (splits > 1) FV_TRY(splitk_reduce(scratch, splits, (size_t)Nout * Kin, alpha_ptr, 1.0f, dW, c.st));
   return 0;
+}
+
+// split-K slabs of dY^T X only: partial[splits][Nout*Kin] (splits = wgrad_splits(...)); summed later in a fixed order
+template <typename AT>
+int wgrad_partial(const Ctx& c, const AT* dY, int Nout, const AT* X, int Kin, int T, int splits, float* partial) {
+  Epilogue e = make_epilogue();
+  e.ldo = Kin;
+  e.out_f32 = partial;
+  if constexpr (std::is_same<AT, float>::value) {
+    return gemm_f32_simt(dY, 1, Nout, X, 1, Kin, Nout, Kin, T, splits, e, c.st);
+  } else {
+    return gemm_bf16_tc(dY, Nout, true, X, Kin, true, Nout, Kin, T, splits, 0, e, c.st);
+  }
 }
 
 PreParams pre_params(const fervit_plan* p) {
@@ -452,6 +475,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   const bool post = !c.norm_first;
   auto GB = [&](int blk, int s) -> float* { return G[p->bslot(blk, s)]; };
   const Dropout nodrop = cx.none();
+  std::vector<AdapterGradJob> ad_jobs;  // adapters whose partial gradients were produced in this call
 
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     if (stage == 0) {
@@ -474,24 +498,29 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       auto DXA = [&](int w) { return (AT*)b.dx_at[w]; };
       auto ATOUT = [&](int w) -> AT* { return F32 ? nullptr : (AT*)b.dx_at[w]; };
       if (!post) {
-        // ---- adapter ----
+        // ---- adapter ----  (AdapterModule backward, hybrid_latent_vit.py:264-265)
         if (A) {
+          // du = alpha * (dy W2) * gelu'(u): one GEMM, derivative and alpha in its epilogue
           Epilogue e = make_epilogue();
-          e.out_f32 = b.p_ad; e.ldo = A;
+          e.act_bwd = ACT_GELU; e.aux = k.ua; e.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); e.out = b.du_ad; e.ldo = A;
           FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_AD2_W), true, e));
-          FV_TRY(adapter_bwd_glue<AT>(b.p_ad, (const AT*)k.ua, (const AT*)k.ga, p->PB(i, FERVIT_B_ALPHA), (size_t)T * A,
-                                      (AT*)b.du_ad, b.ad_part, st));
           if (GB(i, FERVIT_B_AD2_W)) {
             FV_CHECK(GB(i, FERVIT_B_AD2_B) && GB(i, FERVIT_B_AD1_W) && GB(i, FERVIT_B_AD1_B) && GB(i, FERVIT_B_ALPHA),
                      "backward: adapter gradients must be requested together");
-            FV_TRY(wgrad<AT>(cx, DXA(cur), E, (const AT*)k.ga, A, T, p->PB(i, FERVIT_B_ALPHA), GB(i, FERVIT_B_AD2_W),
-                             b.scratch));
-            FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, b.ad_cs, nodrop, st));
-            FV_TRY(adapter_finalize(b.ad_part, adapter_bwd_parts((size_t)T * A), p->PB(i, FERVIT_B_AD2_B), b.ad_cs, E,
-                                    p->PB(i, FERVIT_B_ALPHA), GB(i, FERVIT_B_ALPHA), GB(i, FERVIT_B_AD2_B), st));
-            FV_TRY(wgrad<AT>(cx, (const AT*)b.du_ad, A, (const AT*)k.x2_at, E, T, nullptr, GB(i, FERVIT_B_AD1_W),
-                             b.scratch));
-            FV_TRY(colsum<AT>((const AT*)b.du_ad, T, A, A, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_AD1_B), nodrop, st));
+            // partial sums only; adapter_grad_finalize() below finishes all blocks of this stage group at once
+            const Bufs::AdParts& q = b.ad[i];
+            FV_TRY(wgrad_partial<AT>(cx, DXA(cur), E, (const AT*)k.ga, A, T, q.s2, q.w2_part));
+            FV_TRY(colsum_partial<float>(DX(cur), T, E, E, q.cs_dy, st));
+            FV_TRY(wgrad_partial<AT>(cx, (const AT*)b.du_ad, A, (const AT*)k.x2_at, E, T, q.s1, q.w1_part));
+            FV_TRY(colsum_partial<AT>((const AT*)b.du_ad, T, A, A, q.cs_du, st));
+            AdapterGradJob job;
+            job.w2_part = q.w2_part; job.w1_part = q.w1_part; job.cs_dy = q.cs_dy; job.cs_du = q.cs_du;
+            job.W2 = p->PB(i, FERVIT_B_AD2_W); job.b2 = p->PB(i, FERVIT_B_AD2_B);
+            job.alpha_ptr = p->PB(i, FERVIT_B_ALPHA);
+            job.dW2 = GB(i, FERVIT_B_AD2_W); job.dW1 = GB(i, FERVIT_B_AD1_W); job.db2 = GB(i, FERVIT_B_AD2_B);
+            job.db1 = GB(i, FERVIT_B_AD1_B); job.dalpha = GB(i, FERVIT_B_ALPHA);
+            job.s2 = q.s2; job.s1 = q.s1; job.chunks = q.chunks; job.E = E; job.A = A;
+            ad_jobs.push_back(job);
           }
           e = make_epilogue();
           e.residual = DX(cur); e.out_f32 = DX(cur ^ 1); e.out = ATOUT(cur ^ 1); e.ldo = E;
@@ -663,6 +692,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       }
     }
   }
+  if (!ad_jobs.empty()) FV_TRY(adapter_grad_finalize(ad_jobs.data(), (int)ad_jobs.size(), b.ad_fin, st));
   return 0;
 }
 
