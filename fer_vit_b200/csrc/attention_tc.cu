@@ -50,17 +50,27 @@ template <int LD>
 __device__ __forceinline__ void ldbt(uint32_t (&r)[4], const bf16* M, int np, int kk, int lane) {
   ldsm_x4_t(r, M + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + np * 16 + (lane >> 4) * 8);
 }
-// stage M[S][HD] (global, row stride rs) into smem [32][LD], zero-filling rows S..31
+// stage M[S][HD] (global, row stride rs) into smem [32][LD], zero-filling rows S..31. Asynchronous 16-byte copies
+// (cp.async, L2 -> smem without a register round trip): all ~5 copies per lane and matrix are in flight at once, where
+// a load-then-store loop exposed one global-memory latency per unrolled pair. Caller: stage_wait() before reading.
 template <int HD>
 __device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, size_t rs, int S, int lane) {
   constexpr int CH = HD / 8, LD = Lay<HD>::LD;
-#pragma unroll 2
+#pragma unroll
   for (int i = lane; i < SP * CH; i += 32) {
     const int r = i / CH, c = (i % CH) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < S) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)r * rs + c));
-    *reinterpret_cast<uint4*>(dst + r * LD + c) = v;
+    if (r < S) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + r * LD + c)),
+                   "l"(src + (size_t)r * rs + c)
+                   : "memory");
+    } else {
+      *reinterpret_cast<uint4*>(dst + r * LD + c) = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
+}
+__device__ __forceinline__ void stage_wait() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 }
 
 template <int HD>
@@ -70,6 +80,8 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
   constexpr int MAT = SP * LD;  // elements per staged matrix
+  pdl_trigger();
+  pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.x * WARPS + warp;
@@ -84,7 +96,7 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
   stage<HD>(Qs, Qg, rs, S, lane);
   stage<HD>(Ks, Qg + E, rs, S, lane);
   stage<HD>(Vs, Qg + 2 * E, rs, S, lane);
-  __syncwarp();
+  stage_wait();
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
 #pragma unroll 1
   for (int mt = 0; mt < 2; ++mt) {
@@ -192,6 +204,8 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
   constexpr int MAT = SP * LD;
   constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4;   // Q, K, V, dO (bf16) + LSE, D (fp32), bytes
+  pdl_trigger();
+  pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.x * WARPS + warp;
@@ -232,7 +246,7 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
     Ds[lane] = dsum;
     Ls[lane] = lane < S ? lse[(size_t)bh * S + lane] : INFINITY;
   }
-  __syncwarp();
+  stage_wait();
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
   bf16* dQg = dqkv + (size_t)b * S * rs + h * HD;
   bf16* dKg = dQg + E;
@@ -401,7 +415,8 @@ int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, Drop
     attr = true;
   }
   ProfScope prof(1, (double)B * S * H * HD * 4.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  attn_tc_fwd_kernel<HD><<<ceil_div(B * H, WARPS), WARPS * 32, smem, stream>>>(qkv, out, lse, B, S, H, scale, drop);
+  FV_CUDA(launch_pdl(attn_tc_fwd_kernel<HD>, dim3(ceil_div(B * H, WARPS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
+                     lse, B, S, H, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -417,8 +432,8 @@ int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* 
     attr = true;
   }
   ProfScope prof(1, (double)B * S * H * HD * 8.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  attn_tc_bwd_kernel<HD><<<ceil_div(B * H, WARPS), WARPS * 32, smem, stream>>>(qkv, out, dout, lse, dqkv, B, S, H,
-                                                                              scale, drop);
+  FV_CUDA(launch_pdl(attn_tc_bwd_kernel<HD>, dim3(ceil_div(B * H, WARPS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
+                     dout, lse, dqkv, B, S, H, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

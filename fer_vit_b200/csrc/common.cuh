@@ -49,6 +49,30 @@ extern unsigned long long g_launch_count;
 
 int num_sms();
 
+// Programmatic dependent launch (PDL): kernels launched through launch_pdl() may be scheduled while the previous
+// kernel of the stream is still draining; they call pdl_grid_sync() before touching global memory, so only their
+// launch latency and their input-independent prologue (barrier init, TMEM allocation, descriptor prefetch) overlap the
+// predecessor's tail. FERVIT_PDL=0 turns the launch attribute off (the device-side calls then return immediately).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#if defined(__CUDACC__)
+// let the next kernel of the stream start launching; then wait until the previous one has completed and flushed
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_grid_sync() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // per-kernel-class event timing (runtime.cu); classes: 0 tcgen05 GEMM (flops), 1 attention (bytes),
 // 2 LayerNorm (bytes), 3 fp32 GEMM (flops)
 bool prof_enabled();

@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int rows_per_chunk,
                       float* __restrict__ partial, Dropout drop) {
   __shared__ float4 red[8][32];
+  pdl_trigger();
+  pdl_grid_sync();
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rows_per_chunk;
   const int r1 = min(R, r0 + rows_per_chunk);
@@ -478,7 +480,7 @@ int colsum(const T* in, int R, int C, long long ld, float* scratch, const float*
   const int chunks = colsum_chunks(R);
   const int rpc = ceil_div(R, chunks);
   dim3 grid(ceil_div(C, 128), chunks), block(32, 8);
-  ew::colsum_partial_kernel<T><<<grid, block, 0, stream>>>(in, R, C, ld, rpc, scratch, drop);
+  FV_CUDA(launch_pdl(ew::colsum_partial_kernel<T>, grid, block, 0, stream, in, R, C, ld, rpc, scratch, drop));
   FV_COUNT_LAUNCH();
   ew::colsum_final_kernel<<<ceil_div(C, 128), block, 0, stream>>>(scratch, chunks, C, alpha_ptr, alpha, out);
   FV_COUNT_LAUNCH();
@@ -514,7 +516,8 @@ int colsum_partial(const T* in, int R, int C, long long ld, float* scratch, cuda
   const int chunks = colsum_chunks(R);
   const int rpc = ceil_div(R, chunks);
   dim3 grid(ceil_div(C, 128), chunks), block(32, 8);
-  ew::colsum_partial_kernel<T><<<grid, block, 0, stream>>>(in, R, C, ld, rpc, scratch, make_dropout(0.f, 0, 0));
+  FV_CUDA(launch_pdl(ew::colsum_partial_kernel<T>, grid, block, 0, stream, in, R, C, ld, rpc, scratch,
+                     make_dropout(0.f, 0, 0)));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

@@ -176,6 +176,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int total_kb = (p.K + BK - 1) / BK;
   const int units = m_blocks * n_blocks * p.splits;
 
+  pdl_trigger();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
@@ -201,6 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  pdl_grid_sync();  // the prologue above does not depend on the previous kernel's output
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -431,7 +433,8 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, const Params& 
   const int units = m_blocks * n_blocks * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
   ProfScope prof(0, 2.0 * p.M * (double)p.N * p.K, stream);
-  gemm_tc_kernel<BN, A_MN, B_MN, KIND><<<grid, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  FV_CUDA(launch_pdl(gemm_tc_kernel<BN, A_MN, B_MN, KIND>, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta,
+                     tb, p));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

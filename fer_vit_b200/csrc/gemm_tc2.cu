@@ -106,6 +106,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int units = p.pair_m_blocks * p.n_blocks;
   const int total_kb = (p.K + BK - 1) / BK;
 
+  pdl_trigger();  // the next kernel may start its own prologue while this one runs
   if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -140,6 +141,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // everything above is independent of the previous kernel's output (PDL): wait for it only now
+  pdl_grid_sync();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -469,7 +472,8 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;
   ProfScope prof(0, 2.0 * M * (double)N * K, stream);
-  gemm_tc2_kernel<BN, KIND, F32><<<2 * pairs, THREADS, C::SMEM_BYTES, stream>>>(ta, tb, ty, tz, tx, tr, p);
+  FV_CUDA(launch_pdl(gemm_tc2_kernel<BN, KIND, F32>, dim3(2 * pairs), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta,
+                     tb, ty, tz, tx, tr, p));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

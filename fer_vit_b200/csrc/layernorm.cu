@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               float eps, int rows, int E, float* __restrict__ out_f32, AT* __restrict__ out_at,
               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  pdl_trigger();
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -72,6 +74,8 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
               int rows, int E, float* __restrict__ dx_f32, AT* __restrict__ dx_at, float* __restrict__ partial,
               Dropout at_drop) {
   __shared__ float red[WGRAD ? WARPS * 32 * 4 : 1];
+  pdl_trigger();
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 dg[WGRAD ? CH : 1], db[WGRAD ? CH : 1];
@@ -181,8 +185,8 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float e
   ProfScope prof(2, (double)rows * E * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0,
                  stream);
 #define FV_LN_FWD(CH_)                                                                                          \
-  ln::ln_fwd_kernel<AT, CH_><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(x, gamma, beta, eps, rows, E, \
-                                                                                     out_f32, out_at, mean, rstd)
+  FV_CUDA(launch_pdl(ln::ln_fwd_kernel<AT, CH_>, dim3(ceil_div(rows, ln::WARPS)), dim3(ln::WARPS * 32), 0, stream, x, \
+                     gamma, beta, eps, rows, E, out_f32, out_at, mean, rstd))
   FV_LN_DISPATCH(FV_LN_FWD);
 #undef FV_LN_FWD
   FV_COUNT_LAUNCH();
@@ -209,14 +213,14 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
   if (partial) {
     const int grid = layernorm_bwd_grid(rows);
 #define FV_LN_BWD_W(CH_)                                                                                         \
-  ln::ln_bwd_kernel<DT, AT, true, CH_><<<grid, ln::WARPS * 32, 0, stream>>>(dy, x, mean, rstd, gamma, dres, rows, E, \
-                                                                          dx_f32, dx_at, partial, at_drop)
+  FV_CUDA(launch_pdl(ln::ln_bwd_kernel<DT, AT, true, CH_>, dim3(grid), dim3(ln::WARPS * 32), 0, stream, dy, x, mean,  \
+                     rstd, gamma, dres, rows, E, dx_f32, dx_at, partial, at_drop))
     FV_LN_DISPATCH(FV_LN_BWD_W);
 #undef FV_LN_BWD_W
   } else {
 #define FV_LN_BWD(CH_)                                                                                    \
-  ln::ln_bwd_kernel<DT, AT, false, CH_><<<ceil_div(rows, ln::WARPS), ln::WARPS * 32, 0, stream>>>(        \
-      dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at, nullptr, at_drop)
+  FV_CUDA(launch_pdl(ln::ln_bwd_kernel<DT, AT, false, CH_>, dim3(ceil_div(rows, ln::WARPS)), dim3(ln::WARPS * 32), 0,   \
+                     stream, dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at, (float*)nullptr, at_drop))
     FV_LN_DISPATCH(FV_LN_BWD);
 #undef FV_LN_BWD
   }

@@ -1,6 +1,7 @@
 // Library-wide runtime state: last-error string, SM count, launch counter.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace fervit {
@@ -15,6 +16,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* get_error() { return g_error; }
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FERVIT_PDL"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1;
+}
 
 int num_sms() {
   static int sms = 0;
