@@ -132,8 +132,13 @@ def main():
     ap.add_argument("--profile-only", action="store_true", help="run warm-up + the timed steps and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                                                             "the captured CUDA graph of the step")
+    ap.add_argument("--watchdog", type=int, default=0, help="dump every thread's Python stack to stderr after this "
+                                                             "many seconds and exit (diagnosing multi-GPU hangs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
 
     if args.impl == "reference":
         reference_arm(args)
@@ -268,13 +273,15 @@ def main():
     lib = L.lib()
     roof = None
     hbm = {}
+    # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records and reports
+    torch.cuda.synchronize()
+    psteps = 3
     if rank == 0:
-        torch.cuda.synchronize()
         lib.fervit_profile_enable(1)
-        psteps = 3
-        for i in range(psteps):
-            eager_step(pool_x[i % n_pool], pool_y[i % n_pool])   # per-kernel events need host launches
-        torch.cuda.synchronize()
+    for i in range(psteps):
+        eager_step(pool_x[i % n_pool], pool_y[i % n_pool])   # per-kernel events need host launches
+    torch.cuda.synchronize()
+    if rank == 0:
 
         def read(cls):
             a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
@@ -343,6 +350,15 @@ def main():
                                  "calls_per_step": args.buckets}
         print(json.dumps(line), flush=True)
     if n_gpus > 1:
+        sys.stdout.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if graphed is not None:
+            # ncclCommDestroy blocks while a live CUDA graph still holds captured collectives (observed on 2 x B200:
+            # both ranks parked in destroy_process_group); the benchmark has printed its line, so leave without the
+            # communicator teardown
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 

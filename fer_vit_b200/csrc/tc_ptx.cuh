@@ -43,7 +43,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // arrive on a barrier that may live in another CTA of the cluster (address from mapa)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default .release.cta semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): the .release.cluster form compiles to
+  // MEMBAR.ALL.GPU; TMEM reads are ordered by tcgen05.fence::before_thread_sync, not by this arrive
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -71,6 +73,34 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// try_wait with a suspend-time hint (ns): the thread is parked by the hardware until the phase completes or the hint
+// expires, instead of coming back to the scheduler every few hundred cycles
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Wait used by the single-lane roles (TMA producer, MMA issuer) that share their schedulers with the epilogue warps:
+// polite polling, so a waiting role does not take issue slots from the epilogue math.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("fervit: mbarrier wait timed out (tag %d block %d thread %d parity %u)\n", tag, blockIdx.x, threadIdx.x,
+             parity);
+      __trap();
+    }
+  }
 }
 // Bounded waits: a protocol bug traps (the launch fails loudly) instead of hanging the GPU.
 template <bool CLUSTER>
@@ -200,6 +230,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

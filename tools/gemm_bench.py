@@ -52,7 +52,6 @@ def main():
     ap.add_argument("--iters", type=int, default=15)
     ap.add_argument("--one", default="")
     ap.add_argument("--noflush", action="store_true")
-    ap.add_argument("--epi-sweep", action="store_true")
     ap.add_argument("--kinds", default="plain", help="epilogue families for --sweep: plain,bias,gelu,res_f32")
     ap.add_argument("--sweep", default="", help="M,N,K,bn[;M,N,K,bn...]: time each shape under every isolation flag")
     a = ap.parse_args()
@@ -62,9 +61,6 @@ def main():
         # kernel) and csrc/gemm_tc.cu (bn < 0, single-CTA kernel). kw selects the epilogue family.
         import ctypes
         names = {0: "full", 4: "no epilogue", 5: "mma only", 6: "tma only", 3: "epilogue only"}
-        if a.epi_sweep:
-            names = {3: "epilogue only", 3 | 16: "epi: no tma stores", 3 | 16 | 32: "epi: no stores, no proxy fence",
-                     3 | 64: "epi: stores without wait_group.read", 64: "full without wait_group.read"}
         kws = {"plain": {}, "bias": dict(bias=True), "gelu": dict(act=2, bias=True),
                "res_f32": dict(bias=True, residual=True, out_f32=True)}
         for shape in a.sweep.split(";"):
