@@ -293,9 +293,19 @@ def main():
         lib.fervit_profile_enable(0)
         if g_n:
             achieved = g_flops / (g_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA-fed, TMEM accumulators)",
+            traffic, traffic_note = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
+            if os.path.exists(tpath):
+                tj = json.load(open(tpath))
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch ({tj['launch']}), "
+                                f"algorithmic bytes {tj['algorithmic_bytes_per_launch']}; {tj['note']}")
+            roof = {"bound": "tensor", "kernel": "tc2::gemm_tc2_kernel (CTA-pair tcgen05.mma cta_group::2 kind::f16, "
+                                                 "TMA-fed, TMEM accumulators, TMA-store epilogue) + tc::gemm_tc_kernel "
+                                                 "(single-CTA, MN-major wgrad)",
                     "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": achieved / pk["tflops_sustained"], "traffic": None, "peak_source": pk["source"] +
+                    "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_source": pk["source"] +
                     " (sustained cuBLAS bf16: kernel timed inside a long step)",
                     "launches_per_step": g_n // psteps, "flops_per_step": g_flops / psteps,
                     "ms_per_step_in_kernel": g_ms / psteps,
