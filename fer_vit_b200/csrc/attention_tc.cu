@@ -1,4 +1,5 @@
-// Short-sequence attention on tensor cores for S <= 32 (19 w+ tokens + cls): one warp owns one (sample, head).
+// Short-sequence attention on tensor cores for S <= 32 (19 w+ tokens + cls): two warps own one (sample, head), one per
+// 16-row tile, sharing the staged operands.
 // Q, K, V (and dO) of the head are staged ONCE into shared memory with coalesced 16-byte loads (rows beyond S
 // zero-filled); every MMA operand — including the transposed ones (V for P.V; K, Q, dO for the backward products) —
 // is then fetched with ldmatrix / ldmatrix.trans, so nothing is stored transposed. Q.K^T, P.V and the five backward
@@ -14,7 +15,8 @@ namespace fervit {
 
 namespace attn_tc {
 
-constexpr int WARPS = 4;
+constexpr int HEADS = 4;            // (sample, head) problems per CTA
+constexpr int WARPS = 2 * HEADS;    // two warps per problem: one per 16-row tile of queries (phase 1) / keys (phase 2)
 constexpr int SP = 32;  // padded sequence
 
 template <int HD> struct Lay { static constexpr int LD = HD + 8; };  // row stride (elements): conflict-free ldmatrix
@@ -54,10 +56,10 @@ __device__ __forceinline__ void ldbt(uint32_t (&r)[4], const bf16* M, int np, in
 // (cp.async, L2 -> smem without a register round trip): all ~5 copies per lane and matrix are in flight at once, where
 // a load-then-store loop exposed one global-memory latency per unrolled pair. Caller: stage_wait() before reading.
 template <int HD>
-__device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, size_t rs, int S, int lane) {
+__device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, size_t rs, int S, int t64) {
   constexpr int CH = HD / 8, LD = Lay<HD>::LD;
 #pragma unroll
-  for (int i = lane; i < SP * CH; i += 32) {
+  for (int i = t64; i < SP * CH; i += 64) {
     const int r = i / CH, c = (i % CH) * 8;
     if (r < S) {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + r * LD + c)),
@@ -68,9 +70,10 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, s
     }
   }
 }
-__device__ __forceinline__ void stage_wait() {
+// both warps of a problem have issued their copies: wait for one's own, then meet the partner (named barrier 1 + pair)
+__device__ __forceinline__ void stage_wait(int pair) {
   asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncwarp();
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
 }
 
 template <int HD>
@@ -84,23 +87,24 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
   pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int bh = blockIdx.x * WARPS + warp;
+  const int pair = warp >> 1, wm = warp & 1, t64 = threadIdx.x & 63;
+  const int bh = blockIdx.x * HEADS + pair;
   if (bh >= B * H) return;
   const int b = bh / H, h = bh % H;
   const int E = H * HD;
   const size_t rs = (size_t)3 * E;
   const bf16* Qg = qkv + (size_t)b * S * rs + h * HD;
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 3 * MAT;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw) + (size_t)pair * 3 * MAT;
   bf16* Ks = Qs + MAT;
   bf16* Vs = Ks + MAT;
-  stage<HD>(Qs, Qg, rs, S, lane);
-  stage<HD>(Ks, Qg + E, rs, S, lane);
-  stage<HD>(Vs, Qg + 2 * E, rs, S, lane);
-  stage_wait();
+  stage<HD>(Qs, Qg, rs, S, t64);
+  stage<HD>(Ks, Qg + E, rs, S, t64);
+  stage<HD>(Vs, Qg + 2 * E, rs, S, t64);
+  stage_wait(pair);
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
+  // this warp's 16 query rows (the second warp of a 19-token problem carries 3 live rows: cheap, and in parallel)
 #pragma unroll 1
-  for (int mt = 0; mt < 2; ++mt) {
-    if (mt * 16 >= S) break;
+  for (int mt = wm, once = 0; once < 1 && mt * 16 < S; ++once) {
     float c[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -203,12 +207,13 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
   constexpr int MAT = SP * LD;
-  constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4;   // Q, K, V, dO (bf16) + LSE, D (fp32), bytes
+  constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4;   // per problem: Q, K, V, dO (bf16) + LSE, D (fp32), bytes
   pdl_trigger();
   pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, q = lane & 3;
-  const int bh = blockIdx.x * WARPS + warp;
+  const int pair = warp >> 1, wm = warp & 1, t64 = threadIdx.x & 63;
+  const int bh = blockIdx.x * HEADS + pair;
   if (bh >= B * H) return;
   const int b = bh / H, h = bh % H;
   const int E = H * HD;
@@ -216,17 +221,17 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   const bf16* Qg = qkv + (size_t)b * S * rs + h * HD;
   const bf16* Og = out + (size_t)b * S * E + h * HD;
   const bf16* dOg = dout + (size_t)b * S * E + h * HD;
-  bf16* Qs = reinterpret_cast<bf16*>(smem_raw + (size_t)warp * PER_WARP);
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw + (size_t)pair * PER_WARP);
   bf16* Ks = Qs + MAT;
   bf16* Vs = Ks + MAT;
   bf16* dOs = Vs + MAT;
   float* Ls = reinterpret_cast<float*>(dOs + MAT);
   float* Ds = Ls + SP;
-  stage<HD>(Qs, Qg, rs, S, lane);
-  stage<HD>(Ks, Qg + E, rs, S, lane);
-  stage<HD>(Vs, Qg + 2 * E, rs, S, lane);
-  stage<HD>(dOs, dOg, (size_t)E, S, lane);
-  {
+  stage<HD>(Qs, Qg, rs, S, t64);
+  stage<HD>(Ks, Qg + E, rs, S, t64);
+  stage<HD>(Vs, Qg + 2 * E, rs, S, t64);
+  stage<HD>(dOs, dOg, (size_t)E, S, t64);
+  if (wm == 0) {
     // D_i = dO_i . O_i ; rows beyond S get LSE = +inf so their probabilities vanish
     float dsum = 0.f;
     if (lane < S) {
@@ -246,7 +251,7 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
     Ds[lane] = dsum;
     Ls[lane] = lane < S ? lse[(size_t)bh * S + lane] : INFINITY;
   }
-  stage_wait();
+  stage_wait(pair);
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
   bf16* dQg = dqkv + (size_t)b * S * rs + h * HD;
   bf16* dKg = dQg + E;
@@ -254,8 +259,7 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 
   // ---------------- phase 1: dQ ----------------
 #pragma unroll 1
-  for (int mt = 0; mt < 2; ++mt) {
-    if (mt * 16 >= S) break;
+  for (int mt = wm, once = 0; once < 1 && mt * 16 < S; ++once) {
     float c[4][4], dp[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -322,8 +326,7 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 
   // ---------------- phase 2: dK, dV (rows are keys j, columns are queries i) ----------------
 #pragma unroll 1
-  for (int mt = 0; mt < 2; ++mt) {
-    if (mt * 16 >= S) break;
+  for (int mt = wm, once = 0; once < 1 && mt * 16 < S; ++once) {
     float c[4][4], dp[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -408,14 +411,14 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
 template <int HD>
 int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, Dropout drop, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)HD);
-  constexpr int smem = WARPS * 3 * SP * Lay<HD>::LD * 2;
+  constexpr int smem = HEADS * 3 * SP * Lay<HD>::LD * 2;
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     FV_CUDA(cudaFuncSetAttribute(attn_tc_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
   ProfScope prof(1, (double)B * S * H * HD * 4.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  FV_CUDA(launch_pdl(attn_tc_fwd_kernel<HD>, dim3(ceil_div(B * H, WARPS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
+  FV_CUDA(launch_pdl(attn_tc_fwd_kernel<HD>, dim3(ceil_div(B * H, HEADS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
                      lse, B, S, H, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
@@ -425,14 +428,14 @@ template <int HD>
 int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
                Dropout drop, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)HD);
-  constexpr int smem = WARPS * (4 * SP * Lay<HD>::LD * 2 + 2 * SP * 4);
+  constexpr int smem = HEADS * (4 * SP * Lay<HD>::LD * 2 + 2 * SP * 4);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     FV_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = true;
   }
   ProfScope prof(1, (double)B * S * H * HD * 8.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  FV_CUDA(launch_pdl(attn_tc_bwd_kernel<HD>, dim3(ceil_div(B * H, WARPS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
+  FV_CUDA(launch_pdl(attn_tc_bwd_kernel<HD>, dim3(ceil_div(B * H, HEADS)), dim3(WARPS * 32), (size_t)smem, stream, qkv, out,
                      dout, lse, dqkv, B, S, H, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();

@@ -466,7 +466,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
       }
     }
-    if (lane == 0) tma_store_wait_all<0>();
+    // the staging tiles must outlive their last readers; global visibility comes with grid completion
+    if (lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
