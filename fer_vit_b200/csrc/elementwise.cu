@@ -324,18 +324,35 @@ adapter_grad_phase1_kernel(const __grid_constant__ AdFinBatch b, float* __restri
     *reinterpret_cast<float4*>(j.dW2 + (size_t)i * 4) = make_float4(alpha * a2.x, alpha * a2.y, alpha * a2.z, alpha * a2.w);
     *reinterpret_cast<float4*>(j.dW1 + (size_t)i * 4) = a1;
   }
-  if (blockIdx.x == gridDim.x - 1) {
-    // column sums: db2 = alpha * colsum(dy) [E], db1 = colsum(du) [A]; dalpha += b2 . colsum(dy)
-    for (int c = threadIdx.x; c < j.E; c += blockDim.x) {
-      float cs = 0.f;
-      for (int k = 0; k < j.chunks; ++k) cs += j.cs_dy[(size_t)k * j.E + c];
-      dot += __ldg(j.b2 + c) * cs;
-      j.db2[c] = alpha * cs;
-    }
-    for (int c = threadIdx.x; c < j.A; c += blockDim.x) {
-      float cs = 0.f;
-      for (int k = 0; k < j.chunks; ++k) cs += j.cs_du[(size_t)k * j.A + c];
-      j.db1[c] = cs;
+  {
+    // column sums, spread over the job's CTAs: this CTA owns 32 columns; thread (c, k0) adds chunks k0, k0+8, ...
+    // and the eight partial sums of a column are combined in a fixed order.
+    //   db2 = alpha * colsum(dy) [E], db1 = colsum(du) [A]; dalpha += b2 . colsum(dy)
+    __shared__ float cred[8][33];
+    const int c = threadIdx.x & 31, k0 = threadIdx.x >> 5;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int C = pass == 0 ? j.E : j.A;
+      const float* __restrict__ src = pass == 0 ? j.cs_dy : j.cs_du;
+      for (int c0 = blockIdx.x * 32; c0 < C; c0 += gridDim.x * 32) {
+        const int col = c0 + c;
+        float cs = 0.f;
+        if (col < C)
+          for (int k = k0; k < j.chunks; k += 8) cs += src[(size_t)k * C + col];
+        cred[k0][c] = cs;
+        __syncthreads();
+        if (k0 == 0 && col < C) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) t += cred[w][c];
+          if (pass == 0) {
+            dot += __ldg(j.b2 + col) * t;
+            j.db2[col] = alpha * t;
+          } else {
+            j.db1[col] = t;
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   dot = warp_sum(dot);
