@@ -89,7 +89,8 @@ struct ProfScope {
 // ---------------------------------------------------------------------------------------------
 // Activation ids used by GEMM epilogues and the oracle alike.
 // ---------------------------------------------------------------------------------------------
-enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+// ACT_DERIV (backward only): aux already holds act'(pre), saved by a forward epilogue with pre_is_deriv set
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_DERIV = 3 };
 
 __device__ __forceinline__ float gelu_fwd(float x) {
   // exact-erf GELU: torch nn.GELU() default, timm Mlp, AdapterModule (hybrid_latent_vit.py:259)
@@ -146,6 +147,26 @@ __device__ __forceinline__ float gelu_fwd_poly(float u) {
   p = fmaf(p, s, 3.989227100e-01f);
   return u * fmaf(uc, p, 0.5f);
 }
+// GELU and its derivative in one pass (forward epilogues that save act'(u) for the backward GEMM instead of u):
+// Phi by the polynomial above, the density by one ex2 on the otherwise idle MUFU pipe.
+__device__ __forceinline__ void gelu_fwd_deriv_poly(float u, float& g, float& d) {
+  const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
+  const float s = uc * uc;
+  float p = 3.463219783e-01f / 4294967296.0f;
+  p = fmaf(p, s, -1.879982349e+00f / 268435456.0f);
+  p = fmaf(p, s, 4.556960448e+00f / 16777216.0f);
+  p = fmaf(p, s, -6.600791621e+00f / 1048576.0f);
+  p = fmaf(p, s, 6.482043223e+00f / 65536.0f);
+  p = fmaf(p, s, -4.644546053e+00f / 4096.0f);
+  p = fmaf(p, s, 2.528634271e+00f / 256.0f);
+  p = fmaf(p, s, -1.062569537e+00f / 16.0f);
+  p = fmaf(p, s, 3.989227100e-01f);
+  const float cdf = fmaf(uc, p, 0.5f);
+  float e;  // exp(-u^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * u * (-0.5f * 1.44269504088896340736f)));
+  g = u * cdf;
+  d = fmaf(u * 0.39894228040143267794f, e, cdf);
+}
 __device__ __forceinline__ float gelu_bwd_poly(float u) {
   const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
   const float s = uc * uc;
@@ -167,6 +188,7 @@ __device__ __forceinline__ float act_fwd(int act, float x) {
   return x;
 }
 __device__ __forceinline__ float act_bwd(int act, float pre) {
+  if (act == ACT_DERIV) return pre;
   if (act == ACT_RELU) return pre > 0.0f ? 1.0f : 0.0f;
   if (act == ACT_GELU) return gelu_bwd(pre);
   return 1.0f;
@@ -232,6 +254,7 @@ struct Epilogue {
   void* out;               // activation-dtype output [Mout, ldo] or null
   float* out_f32;          // fp32 output [Mout, ldo] or null
   void* out_pre;           // activation-dtype pre-activation output [M, N] or null
+  int pre_is_deriv;        // 1: out_pre receives act'(pre) instead of pre (the backward GEMM then uses ACT_DERIV)
   int remap_L;             // 0 = rows map 1:1
   const float* pos;        // [(L+1), N] position rows, used with remap_L
   int ldo;                 // leading dimension of out / out_f32 / residual (elements)

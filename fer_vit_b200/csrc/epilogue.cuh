@@ -15,6 +15,7 @@ enum EpiKind {
   EPK_RELU,          // + forward ReLU
   EPK_GELU_BWD,      // accumulator times GELU'(aux)
   EPK_RELU_BWD,      // accumulator times ReLU'(aux)
+  EPK_MUL_BWD,       // accumulator times aux (aux = saved activation derivative, ACT_DERIV)
   EPK_REMAP,         // token rows skip the cls slot, + position rows (input projection)
   EPK_GENERIC,       // everything behind runtime flags (dropout, unusual combinations)
   EPK_COUNT
@@ -29,6 +30,7 @@ static inline int epilogue_kind(const Epilogue& e) {
   if (e.act == ACT_RELU) return EPK_RELU;
   if (e.act_bwd == ACT_GELU) return EPK_GELU_BWD;
   if (e.act_bwd == ACT_RELU) return EPK_RELU_BWD;
+  if (e.act_bwd == ACT_DERIV) return EPK_MUL_BWD;
   return EPK_PLAIN;
 }
 
@@ -68,8 +70,15 @@ __device__ __forceinline__ void epilogue_apply(const Epilogue& e, float alpha, i
   if (GEN ? (e.act != ACT_NONE) : (KIND == EPK_GELU || KIND == EPK_RELU)) {
     if (e.out_pre) {
       AT* p = reinterpret_cast<AT*>(e.out_pre) + (size_t)row * N + col;
+      const int a = GEN ? e.act : (KIND == EPK_GELU ? ACT_GELU : ACT_RELU);
 #pragma unroll
-      for (int i = 0; i < NV; i += 4) store4<AT>(p + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      for (int i = 0; i < NV; i += 4) {
+        if (e.pre_is_deriv)
+          store4<AT>(p + i, make_float4(act_bwd(a, v[i]), act_bwd(a, v[i + 1]), act_bwd(a, v[i + 2]),
+                                        act_bwd(a, v[i + 3])));
+        else
+          store4<AT>(p + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+      }
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {

@@ -52,7 +52,7 @@ constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 template <int BN, int KIND, bool F32>
 struct Cfg {
   static constexpr bool FWD_ACT = (KIND == EPK_GELU || KIND == EPK_RELU);
-  static constexpr bool BWD_ACT = (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD);
+  static constexpr bool BWD_ACT = (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD || KIND == EPK_MUL_BWD);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -83,6 +83,7 @@ struct Params {
   const float* alpha_ptr;
   float alpha;
   int has_out, has_z, has_f32, has_res;
+  int pre_is_deriv;  // forward activations: the Z tile receives act'(pre) instead of pre
   int debug;  // timing experiments only (results are garbage): 1 no TMA loads, 2 no MMAs, 4 no epilogue, 8 record clocks
 };
 
@@ -417,7 +418,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 const float2 f = unpack_bf16x2(aw[t]);
-                if (KIND == EPK_GELU_BWD) {
+                if (KIND == EPK_MUL_BWD) {   // the forward pass saved act'(pre)
+                  v[8 * c + 2 * t] *= f.x;
+                  v[8 * c + 2 * t + 1] *= f.y;
+                } else if (KIND == EPK_GELU_BWD) {
                   v[8 * c + 2 * t] *= gelu_bwd_poly(f.x);
                   v[8 * c + 2 * t + 1] *= gelu_bwd_poly(f.y);
                 } else {
@@ -436,16 +440,39 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           if (C::FWD_ACT) {
-            if (p.has_z) {
-              uint8_t* zrow = Zs + r * 128;
+            uint8_t* zrow = Zs + r * 128;
+            if (p.has_z && p.pre_is_deriv) {
+              // save act'(pre) for the backward GEMM (one multiply there instead of a second polynomial)
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
+              for (int c = 0; c < 8; ++c) {
+                float d[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                  float& x = v[8 * c + t];
+                  if (KIND == EPK_GELU) {
+                    float gg;
+                    gelu_fwd_deriv_poly(x, gg, d[t]);
+                    x = gg;
+                  } else {
+                    d[t] = x > 0.0f ? 1.0f : 0.0f;
+                    x = fmaxf(x, 0.0f);
+                  }
+                }
                 *reinterpret_cast<uint4*>(zrow + ((c ^ sw) << 4)) =
-                    make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
-                               pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
-            }
+                    make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]),
+                               pack_bf16x2(d[6], d[7]));
+              }
+            } else {
+              if (p.has_z) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_poly(v[i]) : fmaxf(v[i], 0.0f);
+                for (int c = 0; c < 8; ++c)
+                  *reinterpret_cast<uint4*>(zrow + ((c ^ sw) << 4)) =
+                      make_uint4(pack_bf16x2(v[8 * c], v[8 * c + 1]), pack_bf16x2(v[8 * c + 2], v[8 * c + 3]),
+                                 pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
+              }
+#pragma unroll
+              for (int i = 0; i < 64; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_poly(v[i]) : fmaxf(v[i], 0.0f);
+            }
           }
           if (p.has_out) {
             uint8_t* yrow = Ys + r * 128;
@@ -547,6 +574,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   p.has_z = zptr != nullptr;
   p.has_f32 = e.out_f32 != nullptr;
   p.has_res = e.residual != nullptr;
+  p.pre_is_deriv = e.pre_is_deriv;
   {
     static int dbg = -1;
     if (dbg != 0) { const char* s = getenv("FERVIT_GEMM_DEBUG"); dbg = s ? (atoi(s) | (1 << 30)) : 0; }
@@ -590,7 +618,8 @@ int gemm_tc2_clock_probe(double* ns, double* cycles) {
 // Can the CTA-pair kernel run this problem? (K-major operands, no split-K, plain / activation epilogues.)
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind) {
   (void)M;
-  if (kind != EPK_PLAIN && kind != EPK_GELU && kind != EPK_RELU && kind != EPK_GELU_BWD && kind != EPK_RELU_BWD)
+  if (kind != EPK_PLAIN && kind != EPK_GELU && kind != EPK_RELU && kind != EPK_GELU_BWD && kind != EPK_RELU_BWD &&
+      kind != EPK_MUL_BWD)
     return false;
   const bool f32 = e.out_f32 != nullptr || e.residual != nullptr;
   if (f32 && kind != EPK_PLAIN) return false;
@@ -600,7 +629,7 @@ bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilog
   if (f32 && e.ldo % 4 != 0) return false;
   auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!al(e.out) || !al(e.out_f32) || !al(e.residual) || !al(e.aux) || !al(e.out_pre) || !al(e.bias)) return false;
-  if ((kind == EPK_GELU_BWD || kind == EPK_RELU_BWD) && e.aux == nullptr) return false;
+  if ((kind == EPK_GELU_BWD || kind == EPK_RELU_BWD || kind == EPK_MUL_BWD) && e.aux == nullptr) return false;
   static int v1 = -1;
   if (v1 < 0) { const char* s = getenv("FERVIT_GEMM_V1"); v1 = (s && atoi(s)) ? 1 : 0; }
   return v1 == 0;
@@ -620,6 +649,7 @@ int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
       case EPK_RELU: FV_TC2_CASE(BN_, EPK_RELU, false);        \
       case EPK_GELU_BWD: FV_TC2_CASE(BN_, EPK_GELU_BWD, false); \
       case EPK_RELU_BWD: FV_TC2_CASE(BN_, EPK_RELU_BWD, false); \
+      case EPK_MUL_BWD: FV_TC2_CASE(BN_, EPK_MUL_BWD, false);   \
       default: break;                                          \
     }                                                          \
   } while (0)

@@ -38,11 +38,11 @@ struct BlockBufs {
   void* ao;     // attention output [T,E] act
   float* x_mid; // pre-norm: x after the attention residual; post-norm: x + sa(x) before norm1   [T,E] fp32
   void* xn2;    // pre-norm: norm2(x_mid); post-norm: norm1 output (MLP input)                   [T,E] act
-  void* u1;     // fc1 pre-activation [T,F] act
+  void* u1;     // act'(fc1 pre-activation) [T,F] act: saved by the forward epilogue, multiplied in by fc2's dgrad
   void* g1;     // fc1 activation (after dropout) [T,F] act
   float* rr2;   // post-norm: x1 + ff(x1) before norm2 [T,E] fp32
   void* x2_at;  // adapter input [T,E] act
-  void* ua;     // adapter pre-activation [T,A] act
+  void* ua;     // act'(adapter pre-activation) [T,A] act
   void* ga;     // adapter activation [T,A] act
 };
 
@@ -411,7 +411,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
       FV_TRY(layernorm_fwd<AT>(k.x_mid, p->PB(i, FERVIT_B_LN2_W), p->PB(i, FERVIT_B_LN2_B), c.eps_block, T, E, nullptr,
                                (AT*)k.xn2, k.m2, k.r2, st));
       e = make_epilogue();
-      e.bias = p->PB(i, FERVIT_B_FC1_B); e.act = c.act; e.out_pre = k.u1; e.out = k.g1; e.ldo = F; e.drop = cx.site(i, 2);
+      e.bias = p->PB(i, FERVIT_B_FC1_B); e.act = c.act; e.out_pre = k.u1; e.pre_is_deriv = 1; e.out = k.g1; e.ldo = F; e.drop = cx.site(i, 2);
       FV_TRY(linear<AT>(cx, (const AT*)k.xn2, T, p->bslot(i, FERVIT_B_FC1_W), false, e));
       e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_FC2_B); e.residual = k.x_mid; e.ldo = E; e.drop = cx.site(i, 3);
@@ -421,7 +421,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
         if (!F32) e.out = k.x2_at;
         FV_TRY(linear<AT>(cx, (const AT*)k.g1, T, p->bslot(i, FERVIT_B_FC2_W), false, e));
         Epilogue d = make_epilogue();
-        d.bias = p->PB(i, FERVIT_B_AD1_B); d.act = ACT_GELU; d.out_pre = k.ua; d.out = k.ga; d.ldo = A;
+        d.bias = p->PB(i, FERVIT_B_AD1_B); d.act = ACT_GELU; d.out_pre = k.ua; d.pre_is_deriv = 1; d.out = k.ga; d.ldo = A;
         FV_TRY(linear<AT>(cx, (const AT*)k.x2_at, T, p->bslot(i, FERVIT_B_AD1_W), false, d));
         Epilogue u = make_epilogue();
         u.bias = p->PB(i, FERVIT_B_AD2_B); u.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); u.residual = x2;
@@ -443,7 +443,7 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
       FV_TRY(layernorm_fwd<AT>(k.x_mid, p->PB(i, FERVIT_B_LN1_W), p->PB(i, FERVIT_B_LN1_B), c.eps_block, T, E, x1,
                                F32 ? nullptr : (AT*)k.xn2, k.m1, k.r1, st));
       e = make_epilogue();
-      e.bias = p->PB(i, FERVIT_B_FC1_B); e.act = c.act; e.out_pre = k.u1; e.out = k.g1; e.ldo = F; e.drop = cx.site(i, 2);
+      e.bias = p->PB(i, FERVIT_B_FC1_B); e.act = c.act; e.out_pre = k.u1; e.pre_is_deriv = 1; e.out = k.g1; e.ldo = F; e.drop = cx.site(i, 2);
       FV_TRY(linear<AT>(cx, (const AT*)k.xn2, T, p->bslot(i, FERVIT_B_FC1_W), false, e));
       e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_FC2_B); e.residual = x1; e.out_f32 = k.rr2; e.ldo = E; e.drop = cx.site(i, 3);
@@ -502,7 +502,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         if (A) {
           // du = alpha * (dy W2) * gelu'(u): one GEMM, derivative and alpha in its epilogue
           Epilogue e = make_epilogue();
-          e.act_bwd = ACT_GELU; e.aux = k.ua; e.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); e.out = b.du_ad; e.ldo = A;
+          e.act_bwd = ACT_DERIV; e.aux = k.ua; e.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); e.out = b.du_ad; e.ldo = A;
           FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_AD2_W), true, e));
           if (GB(i, FERVIT_B_AD2_W)) {
             FV_CHECK(GB(i, FERVIT_B_AD2_B) && GB(i, FERVIT_B_AD1_W) && GB(i, FERVIT_B_AD1_B) && GB(i, FERVIT_B_ALPHA),
@@ -533,7 +533,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
         }
         Epilogue e = make_epilogue();
-        e.act_bwd = c.act; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
+        e.act_bwd = ACT_DERIV; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
         FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_FC2_W), true, e));
         if (GB(i, FERVIT_B_FC1_W)) {
           FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch));
@@ -613,7 +613,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
         }
         Epilogue e = make_epilogue();
-        e.act_bwd = c.act; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
+        e.act_bwd = ACT_DERIV; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
         FV_TRY(linear<AT>(cx, dy2, T, p->bslot(i, FERVIT_B_FC2_W), true, e));
         if (GB(i, FERVIT_B_FC1_W)) {
           FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch));
