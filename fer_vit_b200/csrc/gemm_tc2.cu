@@ -49,7 +49,7 @@ constexpr int YT = 32 * CHUNK * 2;   // bf16 staging tile: 32 rows x 64 B
 constexpr int YT2 = 32 * 64 * 2;     // bf16 staging tile of a 64-column chunk: 32 rows x 128 B
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
-template <int BN, int KIND, bool F32>
+template <int BN, int KIND, int F32>
 struct Cfg {
   static constexpr bool FWD_ACT = (KIND == EPK_GELU || KIND == EPK_RELU);
   static constexpr bool BWD_ACT = (KIND == EPK_GELU_BWD || KIND == EPK_RELU_BWD || KIND == EPK_MUL_BWD);
@@ -60,8 +60,12 @@ struct Cfg {
   //   fp32 kinds (residual / fp32 output): 32-column chunks; X = fp32 tile updated in place (x2), Y = bf16 tile (x2)
   //   bf16 kinds: 64-column chunks (128-byte rows); Y = bf16 out (x1), Z = pre-activation out (x1, forward
   //   activations) or pre-activation in (x2, activation derivatives: the next chunk's tile is in flight)
+  // F32: 0 = bf16 kinds; 1 = fp32 kind, deep operand pipeline; 2 = fp32 kind for K <= 128 (adapter up-projection and
+  // its dgrad: one or two k-blocks): a 2-stage operand ring buys four fp32 tiles per warp, so the residual of a whole
+  // output tile is in flight before the accumulator is even complete
   static constexpr int CW = F32 ? 32 : 64;                     // epilogue chunk width (columns)
-  static constexpr int X_BYTES = F32 ? 2 * XT : 0;
+  static constexpr int XBUF = (F32 == 2) ? 4 : 2;
+  static constexpr int X_BYTES = F32 ? XBUF * XT : 0;
   static constexpr int Y_BYTES = F32 ? 2 * YT : YT2;
   static constexpr int Z_BYTES = F32 ? 0 : (FWD_ACT ? YT2 : (BWD_ACT ? 2 * YT2 : 0));
   static constexpr int WARP_STAGING = X_BYTES + Y_BYTES + Z_BYTES;
@@ -71,8 +75,8 @@ struct Cfg {
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + 1024;  // +1024: manual alignment
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers; 256 or 512 (powers of two)
-  static_assert(STAGES >= 3, "pipeline too shallow");
-  static_assert(2 * STAGES + 4 + 2 * EPI_WARPS + 1 <= BAR_BYTES / 8, "barrier area too small");
+  static_assert(STAGES >= (F32 == 2 ? 2 : 3), "pipeline too shallow");
+  static_assert(2 * STAGES + 4 + 4 * EPI_WARPS + 1 <= BAR_BYTES / 8, "barrier area too small");
   static_assert(!(F32 && KIND != EPK_PLAIN), "fp32 outputs are implemented for the plain epilogue only");
 };
 
@@ -90,7 +94,7 @@ struct Params {
 // [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
 __device__ unsigned long long g_clock_probe[4];
 
-template <int BN, int KIND, bool F32>
+template <int BN, int KIND, int F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -106,8 +110,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* empty_bar = bars + C::STAGES;            // [STAGES]   per CTA
   uint64_t* tmem_full = bars + 2 * C::STAGES;        // [2]        per CTA
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;   // [2]        leader's is the live one
-  uint64_t* ld_bar = bars + 2 * C::STAGES + 4;       // [EPI_WARPS][2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 2 * EPI_WARPS);
+  uint64_t* ld_bar = bars + 2 * C::STAGES + 4;       // [EPI_WARPS][4]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 4 * EPI_WARPS);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,7 +146,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 2 * EPI_WARPS);  // the epilogue warps of BOTH CTAs
     }
-    for (int i = 0; i < 2 * EPI_WARPS; ++i) mbar_init(&ld_bar[i], 1);
+    for (int i = 0; i < 4 * EPI_WARPS; ++i) mbar_init(&ld_bar[i], 1);
     mbar_fence_init();
   }
   if (warp == W_ALLOC) {
@@ -234,7 +238,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint8_t* Xs = wst;
     uint8_t* Ys = wst + C::X_BYTES;
     uint8_t* Zs = wst + C::X_BYTES + C::Y_BYTES;
-    uint64_t* my_ld = ld_bar + ew * 2;
+    uint64_t* my_ld = ld_bar + ew * 4;
     const uint32_t tmem_empty0[2] = {mapa(smem_u32(&tmem_empty[0]), 0), mapa(smem_u32(&tmem_empty[1]), 0)};
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
@@ -262,16 +266,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         // ------------------------------------------------------------------------------------------------
         const bool res = p.has_res != 0;
         const uint32_t xsw = (uint32_t)(r & 7), ysw = (uint32_t)((r >> 1) & 3);
+        constexpr uint32_t XB = C::XBUF;
         auto issue_load = [&](uint32_t gj, int col) {
-          const uint32_t b = gj & 1;
+          const uint32_t b = gj % XB;
           mbar_expect_tx(&my_ld[b], XT);
           tma_load_2d(Xs + b * XT, &tm_r, &my_ld[b], col, row0);
         };
         if (res && lane == 0 && nch > 0) {
-          // the residual of the first two chunks travels while the MMAs of this tile are still running
+          // the residual of the first XBUF chunks travels while the MMAs of this tile are still running
           tma_store_wait_read<0>();  // tiles are updated in place: earlier stores must have drained
-          issue_load(g, col0);
-          if (nch > 1) issue_load(g + 1, col0 + CW);
+          for (int jj = 0; jj < nch && jj < (int)XB; ++jj) issue_load(g + jj, col0 + jj * CW);
         }
         mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
         tc_fence_after();
@@ -285,9 +289,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         tmem_ld32(taddr0, rr);
 #pragma unroll 1
         for (int j = 0; j < nch; ++j, ++g) {
-          const uint32_t b = g & 1;
+          const uint32_t b = g % XB, yb = g & 1;
           const int col = col0 + j * CW;
-          if (res) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
+          if (res) mbar_wait(&my_ld[b], (g / XB) & 1, 5);
           tmem_ld_wait();
           float v[32];
 #pragma unroll
@@ -315,7 +319,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= alpha;
           }
-          // staging tiles [b] were last the source of chunk g-2's stores
+          // the bf16 tile [yb] was last the source of chunk g-2's stores (and, without a residual, the fp32 tile too)
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           uint8_t* xrow = Xs + b * XT + r * 128;
@@ -333,7 +337,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                   make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
           if (p.has_out) {
-            uint8_t* yrow = Ys + b * YT + r * 64;
+            uint8_t* yrow = Ys + yb * YT + r * 64;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
               *reinterpret_cast<uint4*>(yrow + ((c ^ ysw) << 4)) =
@@ -343,12 +347,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (p.has_out) tma_store_2d(&tm_y, Ys + b * YT, col, row0);
+            if (p.has_out) tma_store_2d(&tm_y, Ys + yb * YT, col, row0);
             if (p.has_f32) tma_store_2d(&tm_x, Xs + b * XT, col, row0);
             tma_store_commit();
-            if (res && j + 2 < nch) {
+            if (res && j + (int)XB < nch) {
               tma_store_wait_read<0>();  // the in-place tile must be fully read before it is overwritten
-              issue_load(g + 2, col + 2 * CW);
+              issue_load(g + XB, col + (int)XB * CW);
             }
           }
         }
@@ -557,7 +561,7 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, u
 
 namespace tc2 {
 
-template <int BN, int KIND, bool F32>
+template <int BN, int KIND, int F32>
 static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, const Epilogue& e,
                   cudaStream_t stream) {
   using C = Cfg<BN, KIND, F32>;
@@ -642,14 +646,15 @@ int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
 #define FV_TC2_CASE(BN_, K_, F_) return tc2::launch<BN_, K_, F_>(A, lda, B, ldb, M, N, K, e, stream)
 #define FV_TC2_BN(BN_)                                         \
   do {                                                         \
-    if (f32) FV_TC2_CASE(BN_, EPK_PLAIN, true);                \
+    if (f32 && K <= 128) FV_TC2_CASE(BN_, EPK_PLAIN, 2);       \
+    if (f32) FV_TC2_CASE(BN_, EPK_PLAIN, 1);                   \
     switch (kind) {                                            \
-      case EPK_PLAIN: FV_TC2_CASE(BN_, EPK_PLAIN, false);      \
-      case EPK_GELU: FV_TC2_CASE(BN_, EPK_GELU, false);        \
-      case EPK_RELU: FV_TC2_CASE(BN_, EPK_RELU, false);        \
-      case EPK_GELU_BWD: FV_TC2_CASE(BN_, EPK_GELU_BWD, false); \
-      case EPK_RELU_BWD: FV_TC2_CASE(BN_, EPK_RELU_BWD, false); \
-      case EPK_MUL_BWD: FV_TC2_CASE(BN_, EPK_MUL_BWD, false);   \
+      case EPK_PLAIN: FV_TC2_CASE(BN_, EPK_PLAIN, 0);      \
+      case EPK_GELU: FV_TC2_CASE(BN_, EPK_GELU, 0);        \
+      case EPK_RELU: FV_TC2_CASE(BN_, EPK_RELU, 0);        \
+      case EPK_GELU_BWD: FV_TC2_CASE(BN_, EPK_GELU_BWD, 0); \
+      case EPK_RELU_BWD: FV_TC2_CASE(BN_, EPK_RELU_BWD, 0); \
+      case EPK_MUL_BWD: FV_TC2_CASE(BN_, EPK_MUL_BWD, 0);   \
       default: break;                                          \
     }                                                          \
   } while (0)
