@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--buckets", type=int, default=2)
     ap.add_argument("--profile-only", action="store_true", help="run warm-up + the timed steps and exit (for ncu)")
+    ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                                                             "the captured CUDA graph of the step")
     ap.add_argument("--watchdog", type=int, default=0, help="dump every thread's Python stack to stderr after this "
@@ -174,7 +175,10 @@ def main():
     model = model.to(dev).train()
     bucketer = parallel.enable_data_parallel(model, num_buckets=args.buckets) if n_gpus > 1 else None
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True, capturable=not args.no_graph)
+    if args.torch_optim:
+        opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.01, fused=True, capturable=not args.no_graph)
+    else:
+        opt = fv.FusedAdamW(params, lr=1e-3, weight_decay=0.01)   # the repo's own fused optimizer
 
     # synthetic inputs: a rotating pool larger than the 126 MB L2 (different seed per rank = different shard)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -340,7 +344,8 @@ def main():
                              f"({B}/GPU), NCCL all-reduce of 1,605,907 trainable grads in {args.buckets} buckets "
                              "overlapped with backward"),
                 "global_batch": global_batch, "per_gpu_batch": B, "seq_len": 19, "parallelism": f"dp{n_gpus}",
-                "step": "zero_grad + fwd + CE + bwd + fused AdamW over the trainable set" +
+                "step": "zero_grad + fwd + CE + bwd + fused AdamW over the trainable set (" +
+                        ("torch.optim.AdamW fused" if args.torch_optim else "fer_vit_b200.FusedAdamW") + ")" +
                         ("" if graphed is None else ", replayed from one captured CUDA graph (fer_vit_b200.GraphedTrainStep)"),
                 "l2": f"inputs rotate over a {n_pool * bytes_per_batch / 1e6:.0f} MB pool (> 126 MB L2); the step's own "
                       "activation working set is > 1.5 GB",

@@ -6,8 +6,9 @@ from .models_fer_vit import (LatentViT, LatentViTv2, HybridLatentViT, AdapterMod
                              create_vit_base)
 from .modules import LEAM, SemanticPE, LayerWiseNorm
 from .graph import GraphedTrainStep
+from .optim import FusedAdamW
 
 __all__ = ["set_default_precision", "get_default_precision", "CrossEntropyLoss", "cross_entropy", "LatentViT",
            "LatentViTv2", "HybridLatentViT", "AdapterModule", "create_hybrid_latent_vit", "RECOMMENDED_STRATEGIES",
            "ImageViT", "PatchEmbedding", "create_vit_tiny", "create_vit_small", "create_vit_base", "LEAM",
-           "SemanticPE", "LayerWiseNorm", "GraphedTrainStep"]
+           "SemanticPE", "LayerWiseNorm", "GraphedTrainStep", "FusedAdamW"]

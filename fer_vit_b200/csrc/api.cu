@@ -75,6 +75,19 @@ FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, co
   return gemm_bf16_tc((const bf16*)x, K, false, (const bf16*)W, K, false, M, N, K, 1, force_bn, e, S_(stream));
 }
 
+FV_API long long fervit_adamw_scratch_floats(int n, const long long* numel) {
+  return (n > 0 && numel) ? adamw_scratch_floats(n, numel) : 8;
+}
+
+FV_API int fervit_adamw_step(int n, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                             const long long* numel, const int* group, const float* hyper, float* step, float max_norm,
+                             float* scratch, void* stream) {
+  FV_CHECK(n == 0 || (params && grads && exp_avg && exp_avg_sq && numel && group), "adamw_step: null argument");
+  return adamw_step(n, reinterpret_cast<float* const*>(params), reinterpret_cast<float* const*>(grads),
+                    reinterpret_cast<float* const*>(exp_avg), reinterpret_cast<float* const*>(exp_avg_sq), numel, group,
+                    hyper, step, max_norm, scratch, S_(stream));
+}
+
 FV_API int fervit_debug_gemm_clock(double* ns, double* cycles) {
   FV_CHECK(ns && cycles, "debug_gemm_clock: null argument");
   return gemm_tc2_clock_probe(ns, cycles);

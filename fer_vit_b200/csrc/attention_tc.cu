@@ -119,7 +119,7 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
         uint32_t bb[4];
         ldb<LD>(bb, Ks, np, ks, lane);
         mma16816(c[2 * np], a, bb[0], bb[1]);
-        mma16816(c[2 * np + 1], a, bb[2], bb[3]);
+        if ((2 * np + 1) * 8 < S) mma16816(c[2 * np + 1], a, bb[2], bb[3]);   // skip all-padding key tiles
       }
     }
     // softmax over keys for rows r0 = mt*16+g (elements 0,1) and r1 = r0+8 (elements 2,3)
@@ -276,9 +276,11 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
         ldb<LD>(bk, Ks, np, ks, lane);
         ldb<LD>(bv, Vs, np, ks, lane);
         mma16816(c[2 * np], aq, bk[0], bk[1]);
-        mma16816(c[2 * np + 1], aq, bk[2], bk[3]);
         mma16816(dp[2 * np], ad, bv[0], bv[1]);
-        mma16816(dp[2 * np + 1], ad, bv[2], bv[3]);
+        if ((2 * np + 1) * 8 < S) {   // skip all-padding key tiles
+          mma16816(c[2 * np + 1], aq, bk[2], bk[3]);
+          mma16816(dp[2 * np + 1], ad, bv[2], bv[3]);
+        }
       }
     }
     const int r0 = mt * 16 + g, r1 = r0 + 8;
@@ -343,9 +345,11 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
         ldb<LD>(bq, Qs, np, ks, lane);
         ldb<LD>(bd, dOs, np, ks, lane);
         mma16816(c[2 * np], ak, bq[0], bq[1]);
-        mma16816(c[2 * np + 1], ak, bq[2], bq[3]);
         mma16816(dp[2 * np], av, bd[0], bd[1]);
-        mma16816(dp[2 * np + 1], av, bd[2], bd[3]);
+        if ((2 * np + 1) * 8 < S) {   // skip all-padding query tiles
+          mma16816(c[2 * np + 1], ak, bq[2], bq[3]);
+          mma16816(dp[2 * np + 1], av, bd[2], bd[3]);
+        }
       }
     }
     const int j0 = mt * 16 + g, j1 = j0 + 8;

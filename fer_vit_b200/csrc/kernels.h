@@ -74,6 +74,11 @@ int adapter_finalize(const float* part, int nparts, const float* b2, const float
 int dropout_mask(float* out, size_t n, Dropout drop, cudaStream_t stream);
 int fill_f32(float* out, size_t n, float v, cudaStream_t stream);
 
+// optim.cu
+long long adamw_scratch_floats(int n, const long long* numel);
+int adamw_step(int n, float* const* p, float* const* g, float* const* m, float* const* v, const long long* numel,
+               const int* group, const float* hyper, float* step, float max_norm, float* scratch, cudaStream_t stream);
+
 // attention.cu
 template <typename AT>
 int attention_fwd(const AT* qkv, AT* out, float* lse, int B, int S, int H, int HD, Dropout drop, cudaStream_t stream);

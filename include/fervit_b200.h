@@ -237,6 +237,20 @@ int fervit_dropout_mask(float* out, long long n, float p, unsigned long long see
 #define FERVIT_SITE_INPUT 0xFFFF0u
 #define FERVIT_SITE_HEAD 0xFFFF1u
 
+/* Fused AdamW over n fp32 tensors (device pointer tables live in HOST memory; they are passed to the kernels by
+ * value): torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off) with per-tensor
+ * hyper-parameter groups, the step the reference trainers run right after backward
+ * (train_hybrid_latent_vit.py:63-117, 244-248; clip_grad_norm_ at train_latent_vit_v2.py:132-133).
+ *   hyper: device [groups][5] = lr, beta1, beta2, eps, weight_decay; group[i] selects the row of tensor i
+ *   step : device float, the number of updates done so far (incremented here: capturable in a CUDA graph)
+ *   max_norm > 0: gradients are scaled by min(1, max_norm / (||g||_2 + 1e-6)) over ALL n tensors first (and written
+ *   back scaled, as clip_grad_norm_ leaves them); scratch: fervit_adamw_scratch_floats(n, numel) floats, the clip
+ *   coefficient and the total norm end up in its last two used floats. */
+long long fervit_adamw_scratch_floats(int n, const long long* numel);
+int fervit_adamw_step(int n, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                      const long long* numel, const int* group, const float* hyper, float* step, float max_norm,
+                      float* scratch, void* stream);
+
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 8 set, the CTA-pair GEMM records the wall time (ns, %globaltimer) and the SM
  * cycle count (clock64) of its CTA 0; cycles / ns = the SM clock in GHz while the kernel ran. */
 int fervit_debug_gemm_clock(double* ns, double* cycles);

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/parity_metrics.jsonl
 nvidia-smi --query-gpu=name,driver_version,clocks.sm,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
 declare -A G
-G[ops_basic]="tests/test_gpu_ops.py -k 'simt or layernorm or attention or cross_entropy or premodules'"
+G[ops_basic]="tests/test_gpu_ops.py -k 'simt or layernorm or attention or cross_entropy or premodules or adamw'"
 G[ops_tc]="tests/test_gpu_ops.py -k 'tcgen05'"
 G[ops_wgrad]="tests/test_gpu_ops.py -k 'wgrad'"
 G[models_fp32]="tests/test_gpu_models.py -k 'fp32 or fallback or roundtrip or graphed or fused'"

@@ -344,3 +344,43 @@ def test_premodules(lib, flags, B, D):
         errs["d" + n] = relerr(a, b)
     record("premodules", flags=list(flags), B=B, D=D, worst=max(errs.values()))
     assert max(errs.values()) < 2e-5, errs
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+@pytest.mark.parametrize("max_norm", [None, 0.5])
+def test_fused_adamw_matches_torch(lib, max_norm):
+    """fer_vit_b200.FusedAdamW against torch.optim.AdamW (+ clip_grad_norm_) on two hyper-parameter groups, ragged
+    tensor sizes, four steps with fresh gradients; also the state_dict round trip."""
+    import fer_vit_b200 as fv
+    g = torch.Generator(device="cuda").manual_seed(7)
+    shapes = [(768, 64), (64,), (1,), (5, 4097), (19, 768), (7, 768)]
+    ref = [torch.nn.Parameter(torch.randn(*s, device="cuda", generator=g)) for s in shapes]
+    our = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+
+    def groups(ps):
+        return [dict(params=ps[:3], lr=3e-3, weight_decay=0.05), dict(params=ps[3:], lr=1e-2, betas=(0.8, 0.95))]
+    o_ref = torch.optim.AdamW(groups(ref), lr=1e-3, weight_decay=0.01)
+    o_our = fv.FusedAdamW(groups(our), lr=1e-3, weight_decay=0.01, max_grad_norm=max_norm)
+    for step in range(4):
+        if step == 2:   # a scheduler-style change
+            for o in (o_ref, o_our):
+                o.param_groups[0]["lr"] = 1e-3
+            sd = o_our.state_dict()
+            o_our = fv.FusedAdamW(groups(our), lr=1e-3, weight_decay=0.01, max_grad_norm=max_norm)
+            o_our.load_state_dict(sd)
+        for a, b in zip(ref, our):
+            gr = torch.randn(a.shape, device="cuda", generator=g) * (1 + step)
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        if max_norm:
+            tn = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        o_ref.step()
+        o_our.step()
+        if max_norm:
+            assert abs(float(o_our.last_total_norm) - float(tn)) <= 1e-5 * float(tn)
+            for a, b in zip(ref, our):
+                assert relerr(b.grad, a.grad) < 1e-6, "gradients are left clipped, as clip_grad_norm_ leaves them"
+    torch.cuda.synchronize()
+    errs = [relerr(b, a) for a, b in zip(ref, our)]
+    record("fused_adamw", max_norm=max_norm or 0.0, err=max(errs))
+    assert max(errs) < 2e-6, errs

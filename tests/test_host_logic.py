@@ -187,3 +187,13 @@ def test_weighted_ce_is_rank_invariant_under_dp():
         loss = -(lp[torch.arange(4), y[sl]] * w[y[sl]]).sum() / den_local
         parts.append(torch.autograd.grad(loss, zz)[0] / 2)    # all-reduce AVG
     assert torch.allclose(torch.cat(parts), full, atol=1e-12)
+
+
+def test_fused_adamw_has_no_cpu_fallback():
+    import fer_vit_b200 as fv
+    p = torch.nn.Parameter(torch.randn(4, 4))
+    opt = fv.FusedAdamW([p], lr=1e-3)
+    assert opt.defaults["capturable"] is True
+    p.grad = torch.randn(4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        opt.step()
