@@ -13,6 +13,7 @@
 #include "fervit_b200.h"
 #include <type_traits>
 #include <vector>
+#include <stdlib.h>
 
 namespace fervit {
 
@@ -85,6 +86,16 @@ struct fervit_plan {
   size_t wcache_bytes;
   char* wcache;
   int bwd_cur;  // which of dx[0]/dx[1] holds the running gradient between backward stages
+  // Side stream of the backward pass: the adapter weight-gradient GEMMs and column sums do not feed the dgrad chain,
+  // so they run beside it and fill the SMs the chain leaves idle (57-tile GEMMs, partial last waves). Fork/join by
+  // events; inside a CUDA-graph capture this becomes a parallel branch of the graph.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~fervit_plan() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+  }
 
   int nslots() const { return FERVIT_NUM_GLOBAL + cfg.depth * FERVIT_NUM_BLOCK; }
   static int bslot(int blk, int s) { return FERVIT_NUM_GLOBAL + blk * FERVIT_NUM_BLOCK + s; }
@@ -337,6 +348,12 @@ int wgrad_partial(const Ctx& c, const AT* dY, int Nout, const AT* X, int Kin, in
   }
 }
 
+bool use_side_stream() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FERVIT_SIDE_STREAM"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  return on == 1 && !prof_enabled();   // the per-kernel event profile wants one serial stream
+}
+
 PreParams pre_params(const fervit_plan* p) {
   PreParams q;
   const fervit_config& c = p->cfg;
@@ -476,6 +493,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   auto GB = [&](int blk, int s) -> float* { return G[p->bslot(blk, s)]; };
   const Dropout nodrop = cx.none();
   std::vector<AdapterGradJob> ad_jobs;  // adapters whose partial gradients were produced in this call
+  bool side_pending = false;            // side-stream work of the current block not yet joined
 
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     if (stage == 0) {
@@ -507,12 +525,29 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           if (GB(i, FERVIT_B_AD2_W)) {
             FV_CHECK(GB(i, FERVIT_B_AD2_B) && GB(i, FERVIT_B_AD1_W) && GB(i, FERVIT_B_AD1_B) && GB(i, FERVIT_B_ALPHA),
                      "backward: adapter gradients must be requested together");
-            // partial sums only; adapter_grad_finalize() below finishes all blocks of this stage group at once
+            // partial sums only; adapter_grad_finalize() below finishes all blocks of this stage group at once.
+            // They read dy (DX/DXA(cur)) and du, which the main chain overwrites only at norm2's backward: fork
+            // here, join there.
             const Bufs::AdParts& q = b.ad[i];
-            FV_TRY(wgrad_partial<AT>(cx, DXA(cur), E, (const AT*)k.ga, A, T, q.s2, q.w2_part));
-            FV_TRY(colsum_partial<float>(DX(cur), T, E, E, q.cs_dy, st));
-            FV_TRY(wgrad_partial<AT>(cx, (const AT*)b.du_ad, A, (const AT*)k.x2_at, E, T, q.s1, q.w1_part));
-            FV_TRY(colsum_partial<AT>((const AT*)b.du_ad, T, A, A, q.cs_du, st));
+            cudaStream_t ws = st;
+            if (use_side_stream()) {
+              if (!p->side) {
+                FV_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+                FV_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                FV_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+              }
+              FV_CUDA(cudaEventRecord(p->ev_fork, st));
+              FV_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+              ws = p->side;
+              side_pending = true;
+            }
+            Ctx cw = cx;
+            cw.st = ws;
+            FV_TRY(wgrad_partial<AT>(cw, DXA(cur), E, (const AT*)k.ga, A, T, q.s2, q.w2_part));
+            FV_TRY(colsum_partial<float>(DX(cur), T, E, E, q.cs_dy, ws));
+            FV_TRY(wgrad_partial<AT>(cw, (const AT*)b.du_ad, A, (const AT*)k.x2_at, E, T, q.s1, q.w1_part));
+            FV_TRY(colsum_partial<AT>((const AT*)b.du_ad, T, A, A, q.cs_du, ws));
+            if (side_pending) FV_CUDA(cudaEventRecord(p->ev_join, p->side));
             AdapterGradJob job;
             job.w2_part = q.w2_part; job.w1_part = q.w1_part; job.cs_dy = q.cs_dy; job.cs_du = q.cs_du;
             job.W2 = p->PB(i, FERVIT_B_AD2_W); job.b2 = p->PB(i, FERVIT_B_AD2_B);
@@ -542,6 +577,10 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         e = make_epilogue();
         e.out = b.d_e1; e.ldo = E;
         FV_TRY(linear<AT>(cx, (const AT*)b.d_big, T, p->bslot(i, FERVIT_B_FC1_W), true, e));
+        if (side_pending) {  // norm2's backward overwrites the gradient buffers the side stream reads
+          FV_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
+          side_pending = false;
+        }
         {
           float* part = GB(i, FERVIT_B_LN2_W) ? b.scratch : nullptr;
           FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, k.x_mid, k.m2, k.r2, p->PB(i, FERVIT_B_LN2_W), DX(cur), T, E,
