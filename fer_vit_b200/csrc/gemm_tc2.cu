@@ -166,8 +166,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int u = pair_id; u < units; u += num_pairs) {
-        const int pm = u % p.pair_m_blocks;
-        const int n_blk = u / p.pair_m_blocks;
+        // n fastest: the pairs running at one time share a band of A rows across all n-blocks, so A (the big
+        // operand: activations) streams from HBM once and the weights (<= 14 MB) stay in L2. With m fastest, A was
+        // re-read once per n-block as soon as it outgrew the 126 MB L2 (K = 3072 at batch >= 1024: TMA+MMA 143 us
+        // against 107 us of MMAs alone, profiles/).
+        const int n_blk = u % p.n_blocks;
+        const int pm = u / p.n_blocks;
         const int row_a = pm * (2 * BM) + (int)rank * BM;
         const int row_b = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < total_kb; ++kb) {
@@ -246,8 +250,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint32_t g = 0;  // chunks processed so far: double-buffered tiles use g & 1, load-barrier parity = (g >> 1) & 1
     int it = 0;
     for (int u = pair_id; u < units; u += num_pairs, ++it) {
-      const int pm = u % p.pair_m_blocks;
-      const int n_blk = u / p.pair_m_blocks;
+      const int n_blk = u % p.n_blocks;
+      const int pm = u / p.n_blocks;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = pm * (2 * BM) + (int)rank * BM + quarter * 32;
