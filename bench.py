@@ -280,15 +280,21 @@ def main():
     # every rank runs these steps (they contain the gradient all-reduce); only rank 0 records and reports
     torch.cuda.synchronize()
     psteps = 3
-    if rank == 0:
-        lib.fervit_profile_enable(1)
+    # the serial host-launched step the per-launch events belong to (the timed region above replays a graph, where
+    # PDL and the side stream overlap kernels): timed first without the per-kernel events, which slow the host down
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eager_step(pool_x[0], pool_y[0])
     pe0.record()
     for i in range(psteps):
-        eager_step(pool_x[i % n_pool], pool_y[i % n_pool])   # per-kernel events need host launches
+        eager_step(pool_x[i % n_pool], pool_y[i % n_pool])
     pe1.record()
     torch.cuda.synchronize()
-    profile_step_ms = pe0.elapsed_time(pe1) / psteps   # the serial, event-instrumented step the kernel times belong to
+    profile_step_ms = pe0.elapsed_time(pe1) / psteps
+    if rank == 0:
+        lib.fervit_profile_enable(1)
+    for i in range(psteps):
+        eager_step(pool_x[i % n_pool], pool_y[i % n_pool])   # per-kernel events need host launches
+    torch.cuda.synchronize()
     if rank == 0:
 
         def read(cls):
@@ -317,10 +323,9 @@ def main():
                     " (sustained cuBLAS bf16: kernel timed inside a long step)",
                     "launches_per_step": g_n // psteps, "flops_per_step": g_flops / psteps,
                     "ms_per_step_in_kernel": g_ms / psteps,
-                    # share of the SAME serial eager pass the per-launch events were taken in (the timed region above
-                    # replays a graph with PDL and a side stream, where kernels overlap); compare with the ncu launch list
+                    # share of the serial host-launched step (compare with the ncu launch list in profiles/)
                     "share_of_step": (g_ms / psteps) / profile_step_ms,
-                    "profile_pass_ms_per_step": profile_step_ms}
+                    "eager_ms_per_step": profile_step_ms}
         if a_n:
             hbm["attention"] = {"achieved_gbs": a_bytes / (a_ms * 1e-3) / 1e9, "frac": a_bytes / (a_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                 "ms_per_step": a_ms / psteps, "launches_per_step": a_n // psteps}

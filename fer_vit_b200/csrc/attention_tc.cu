@@ -52,6 +52,11 @@ template <int LD>
 __device__ __forceinline__ void ldbt(uint32_t (&r)[4], const bf16* M, int np, int kk, int lane) {
   ldsm_x4_t(r, M + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + np * 16 + (lane >> 4) * 8);
 }
+// A fragment of the TRANSPOSE: rows m in [mt*16, +16), k in [kk*16, +16), from a matrix stored as M[k][m] (m contiguous)
+template <int LD>
+__device__ __forceinline__ void lda_t(uint32_t (&a)[4], const bf16* M, int mt, int kk, int lane) {
+  ldsm_x4_t(a, M + (kk * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * LD + mt * 16 + ((lane >> 3) & 1) * 8);
+}
 // stage M[S][HD] (global, row stride rs) into smem [32][LD], zero-filling rows S..31. Asynchronous 16-byte copies
 // (cp.async, L2 -> smem without a register round trip): all ~5 copies per lane and matrix are in flight at once, where
 // a load-then-store loop exposed one global-memory latency per unrolled pair. Caller: stage_wait() before reading.
@@ -197,8 +202,10 @@ attn_tc_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* 
   }
 }
 
-// Backward. Phase 1 (query-major): S = Q K^T, dP = dO V^T -> dS -> dQ = dS K.
-//           Phase 2 (key-major):   S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T -> dV = P^T dO, dK = dS^T Q.
+// Backward. Phase 1 (query-major, one 16-query tile per warp): S = Q K^T, dP = dO V^T -> P~, dS -> dQ = dS K; P~ and dS
+//           are also parked in shared memory (bf16, [query][key]).
+//           Phase 2 (key-major, one 16-key tile per warp): dV = P~^T dO, dK = dS^T Q with the A operands fetched
+//           TRANSPOSED from the parked tiles (ldmatrix.trans) instead of recomputing S^T and dP^T.
 template <int HD>
 __global__ void __launch_bounds__(WARPS * 32)
 attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
@@ -207,7 +214,9 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   extern __shared__ __align__(16) uint8_t smem_raw[];
   constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
   constexpr int MAT = SP * LD;
-  constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4;   // per problem: Q, K, V, dO (bf16) + LSE, D (fp32), bytes
+  constexpr int LDP = SP + 8;                          // row stride of the parked P~ / dS tiles (elements)
+  // per problem: Q, K, V, dO (bf16) + LSE, D (fp32) + P~, dS (bf16), bytes
+  constexpr int PER_WARP = 4 * MAT * 2 + 2 * SP * 4 + 2 * SP * LDP * 2;
   pdl_trigger();
   pdl_grid_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -227,6 +236,8 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
   bf16* dOs = Vs + MAT;
   float* Ls = reinterpret_cast<float*>(dOs + MAT);
   float* Ds = Ls + SP;
+  bf16* Ps = reinterpret_cast<bf16*>(Ds + SP);
+  bf16* dSs = Ps + SP * LDP;
   stage<HD>(Qs, Qg, rs, S, t64);
   stage<HD>(Ks, Qg + E, rs, S, t64);
   stage<HD>(Vs, Qg + 2 * E, rs, S, t64);
@@ -291,13 +302,25 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
       for (int e = 0; e < 4; ++e) {
         const int row = (e >> 1) ? r1 : r0, col = nt * 8 + 2 * q + (e & 1);
         const float p = col < S ? __expf(c[nt][e] * scale - ((e >> 1) ? l1 : l0)) : 0.f;
-        float dpv = dp[nt][e];
+        float dpv = dp[nt][e], ptv = p;
         if (drop.threshold) {
           const uint64_t idx = ((uint64_t)bh * S + row) * S + col;
-          dpv = drop_keep(dseed, drop.site, idx, drop.threshold) ? dpv * drop.scale : 0.f;
+          const bool keep = drop_keep(dseed, drop.site, idx, drop.threshold);
+          dpv = keep ? dpv * drop.scale : 0.f;
+          ptv = keep ? p * drop.scale : 0.f;
         }
         c[nt][e] = p * (dpv - ((e >> 1) ? d1v : d0v)) * scale;   // dS
+        dp[nt][e] = ptv;                                         // P~ (dropout applied), reused below
       }
+    // park P~ and dS for phase 2 (rows beyond S are zero: their LSE is +inf)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int col = nt * 8 + 2 * q;
+      *reinterpret_cast<uint32_t*>(Ps + r0 * LDP + col) = pack_bf16x2(dp[nt][0], dp[nt][1]);
+      *reinterpret_cast<uint32_t*>(Ps + r1 * LDP + col) = pack_bf16x2(dp[nt][2], dp[nt][3]);
+      *reinterpret_cast<uint32_t*>(dSs + r0 * LDP + col) = pack_bf16x2(c[nt][0], c[nt][1]);
+      *reinterpret_cast<uint32_t*>(dSs + r1 * LDP + col) = pack_bf16x2(c[nt][2], c[nt][3]);
+    }
     float dq[ND][4];
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd)
@@ -326,50 +349,19 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
     }
   }
 
-  // ---------------- phase 2: dK, dV (rows are keys j, columns are queries i) ----------------
+  // ---------------- phase 2: dK, dV (rows are keys j; the reduction runs over queries i) ----------------
+  if (wm * 16 >= S) {
+    // this warp had no query tile: its half of the parked tiles is still unwritten
+#pragma unroll
+    for (int i = lane; i < 16 * (LDP / 2); i += 32) {
+      reinterpret_cast<uint32_t*>(Ps + 16 * LDP)[i] = 0u;
+      reinterpret_cast<uint32_t*>(dSs + 16 * LDP)[i] = 0u;
+    }
+  }
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");   // both query tiles are parked
 #pragma unroll 1
   for (int mt = wm, once = 0; once < 1 && mt * 16 < S; ++once) {
-    float c[4][4], dp[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) { c[nt][e] = 0.f; dp[nt][e] = 0.f; }
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t ak[4], av[4];
-      lda<LD>(ak, Ks, mt, ks, lane);
-      lda<LD>(av, Vs, mt, ks, lane);
-#pragma unroll
-      for (int np = 0; np < 2; ++np) {
-        uint32_t bq[4], bd[4];
-        ldb<LD>(bq, Qs, np, ks, lane);
-        ldb<LD>(bd, dOs, np, ks, lane);
-        mma16816(c[2 * np], ak, bq[0], bq[1]);
-        mma16816(dp[2 * np], av, bd[0], bd[1]);
-        if ((2 * np + 1) * 8 < S) {   // skip all-padding query tiles
-          mma16816(c[2 * np + 1], ak, bq[2], bq[3]);
-          mma16816(dp[2 * np + 1], av, bd[2], bd[3]);
-        }
-      }
-    }
     const int j0 = mt * 16 + g, j1 = j0 + 8;
-    float pt[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = (e >> 1) ? j1 : j0, i = nt * 8 + 2 * q + (e & 1);
-        const float p = (j < S) ? __expf(c[nt][e] * scale - Ls[i]) : 0.f;   // Ls[i >= S] = +inf -> 0
-        float ptv = p, dpv = dp[nt][e];
-        if (drop.threshold) {
-          const uint64_t idx = ((uint64_t)bh * S + i) * S + j;
-          const bool keep = drop_keep(dseed, drop.site, idx, drop.threshold);
-          ptv = keep ? p * drop.scale : 0.f;
-          dpv = keep ? dpv * drop.scale : 0.f;
-        }
-        pt[nt][e] = ptv;                                   // P~^T
-        c[nt][e] = p * (dpv - Ds[i]) * scale;              // dS^T
-      }
     float dv[ND][4], dk[ND][4];
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd)
@@ -377,15 +369,10 @@ attn_tc_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, c
       for (int e = 0; e < 4; ++e) { dv[nd][e] = 0.f; dk[nd][e] = 0.f; }
 #pragma unroll
     for (int kk = 0; kk < 2; ++kk) {
+      if (kk * 16 >= S) break;   // all-padding query block
       uint32_t ap[4], as[4];
-      ap[0] = pack_bf16x2(pt[2 * kk][0], pt[2 * kk][1]);
-      ap[1] = pack_bf16x2(pt[2 * kk][2], pt[2 * kk][3]);
-      ap[2] = pack_bf16x2(pt[2 * kk + 1][0], pt[2 * kk + 1][1]);
-      ap[3] = pack_bf16x2(pt[2 * kk + 1][2], pt[2 * kk + 1][3]);
-      as[0] = pack_bf16x2(c[2 * kk][0], c[2 * kk][1]);
-      as[1] = pack_bf16x2(c[2 * kk][2], c[2 * kk][3]);
-      as[2] = pack_bf16x2(c[2 * kk + 1][0], c[2 * kk + 1][1]);
-      as[3] = pack_bf16x2(c[2 * kk + 1][2], c[2 * kk + 1][3]);
+      lda_t<LDP>(ap, Ps, mt, kk, lane);    // P~^T  [keys x queries]
+      lda_t<LDP>(as, dSs, mt, kk, lane);   // dS^T
 #pragma unroll
       for (int np = 0; np < ND / 2; ++np) {
         uint32_t bo[4], bq[4];
@@ -432,7 +419,7 @@ template <int HD>
 int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
                Dropout drop, cudaStream_t stream) {
   const float scale = 1.0f / sqrtf((float)HD);
-  constexpr int smem = HEADS * (4 * SP * Lay<HD>::LD * 2 + 2 * SP * 4);
+  constexpr int smem = HEADS * (4 * SP * Lay<HD>::LD * 2 + 2 * SP * 4 + 2 * SP * (SP + 8) * 2);
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     FV_CUDA(cudaFuncSetAttribute(attn_tc_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -316,7 +316,8 @@ int head_wgrad_chunks(int B) {
 template <typename AT>
 int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const float* gamma, const float* beta,
              const float* W, int C, const float* mean, const float* rstd, Dropout drop, float* dx_f32, AT* dx_at,
-             int wgrad, float* scratch, float* dW, float* dgamma, float* dbeta, float* dbias, cudaStream_t stream) {
+             int wgrad, float* scratch, float* dW, float* dgamma, float* dbeta, float* dbias, cudaStream_t stream,
+             cudaStream_t wgrad_stream) {
   FV_CHECK(E % 4 == 0 && E <= head::MAXCH * 128, "head: E must be a multiple of 4 and <= 1024 (got %d)", E);
   FV_CHECK(C >= 1 && C <= head::MAXC, "head: num_classes must be in [1, %d] (got %d)", head::MAXC, C);
   head::head_bwd_dx_kernel<AT><<<ceil_div(B, 4), 128, 0, stream>>>(x, dlogits, B, S, E, gamma, W, C, mean, rstd, drop,
@@ -326,11 +327,12 @@ int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const fl
     const int chunks = head_wgrad_chunks(B);
     const int bpc = ceil_div(B, chunks);
     dim3 grid(ceil_div(E, 128), chunks);
-    head::head_wgrad_partial_kernel<<<grid, 128, 0, stream>>>(x, dlogits, B, S, E, gamma, beta, W, C, mean, rstd, drop,
-                                                             bpc, scratch);
+    // the parameter gradients do not feed the dgrad chain: the caller may put them on a side stream
+    head::head_wgrad_partial_kernel<<<grid, 128, 0, wgrad_stream>>>(x, dlogits, B, S, E, gamma, beta, W, C, mean, rstd,
+                                                                   drop, bpc, scratch);
     FV_COUNT_LAUNCH();
-    head::head_wgrad_final_kernel<<<ceil_div((C + 2) * E, 256), 256, 0, stream>>>(scratch, chunks, C, E, dlogits, B, dW,
-                                                                                 dgamma, dbeta, dbias);
+    head::head_wgrad_final_kernel<<<ceil_div((C + 2) * E, 256), 256, 0, wgrad_stream>>>(scratch, chunks, C, E, dlogits, B,
+                                                                                       dW, dgamma, dbeta, dbias);
     FV_COUNT_LAUNCH();
   }
   FV_LAUNCH_CHECK();
@@ -338,10 +340,10 @@ int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const fl
 }
 template int head_bwd<float>(const float*, const float*, int, int, int, const float*, const float*, const float*, int,
                              const float*, const float*, Dropout, float*, float*, int, float*, float*, float*, float*,
-                             float*, cudaStream_t);
+                             float*, cudaStream_t, cudaStream_t);
 template int head_bwd<bf16>(const float*, const float*, int, int, int, const float*, const float*, const float*, int,
                             const float*, const float*, Dropout, float*, bf16*, int, float*, float*, float*, float*,
-                            float*, cudaStream_t);
+                            float*, cudaStream_t, cudaStream_t);
 
 int cross_entropy(const float* logits, const long long* labels, const float* weight, float smoothing, int B, int C,
                   const float* den_in, float grad_scale, float* loss, float* dlogits, float* den_out,

@@ -100,7 +100,8 @@ int head_wgrad_chunks(int B);
 template <typename AT>
 int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const float* gamma, const float* beta,
              const float* W, int C, const float* mean, const float* rstd, Dropout drop, float* dx_f32, AT* dx_at,
-             int wgrad, float* scratch, float* dW, float* dgamma, float* dbeta, float* dbias, cudaStream_t stream);
+             int wgrad, float* scratch, float* dW, float* dgamma, float* dbeta, float* dbias, cudaStream_t stream,
+             cudaStream_t wgrad_stream);
 int cross_entropy(const float* logits, const long long* labels, const float* weight, float smoothing, int B, int C,
                   const float* den_in, float grad_scale, float* loss, float* dlogits, float* den_out,
                   cudaStream_t stream);

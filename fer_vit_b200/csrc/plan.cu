@@ -67,6 +67,7 @@ struct Bufs {
   struct AdParts { float *w2_part, *w1_part, *cs_dy, *cs_du; int s2, s1, chunks; };
   std::vector<AdParts> ad;
   float* ad_fin;               // scratch of adapter_grad_finalize
+  float* head_scratch;         // partial sums of the head's parameter gradients (own buffer: may run on the side stream)
   float* scratch;
   size_t scratch_floats;
 };
@@ -90,10 +91,11 @@ struct fervit_plan {
   // so they run beside it and fill the SMs the chain leaves idle (57-tile GEMMs, partial last waves). Fork/join by
   // events; inside a CUDA-graph capture this becomes a parallel branch of the graph.
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_tail = nullptr;
   ~fervit_plan() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_tail) cudaEventDestroy(ev_tail);
     if (side) cudaStreamDestroy(side);
   }
 
@@ -279,6 +281,7 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
     }
     b.dtok = ar.take<AT>(Tl * E);
     b.dain = p->has_pre ? (void*)ar.take<AT>(Tl * c.Din) : nullptr;
+    b.head_scratch = ar.take<float>((size_t)head_wgrad_chunks(B) * (c.C + 2) * E);
     b.scratch_floats = scratch_floats_for(p, B);
     b.scratch = ar.take<float>(b.scratch_floats);
   }
@@ -346,6 +349,16 @@ int wgrad_partial(const Ctx& c, const AT* dY, int Nout, const AT* X, int Kin, in
   } else {
     return gemm_bf16_tc(dY, Nout, true, X, Kin, true, Nout, Kin, T, splits, 0, e, c.st);
   }
+}
+
+int ensure_side_stream(fervit_plan* p) {
+  if (!p->side) {
+    FV_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    FV_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    FV_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    FV_CUDA(cudaEventCreateWithFlags(&p->ev_tail, cudaEventDisableTiming));
+  }
+  return 0;
 }
 
 bool use_side_stream() {
@@ -494,6 +507,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   const Dropout nodrop = cx.none();
   std::vector<AdapterGradJob> ad_jobs;  // adapters whose partial gradients were produced in this call
   bool side_pending = false;            // side-stream work of the current block not yet joined
+  bool side_used = false;               // anything at all went to the side stream in this call
 
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     if (stage == 0) {
@@ -504,10 +518,18 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       if (wg)
         FV_CHECK(G[FERVIT_G_HEAD_B] && G[FERVIT_G_HEAD_LN_W] && G[FERVIT_G_HEAD_LN_B],
                  "backward: head gradients must be requested together");
+      cudaStream_t hs = st;
+      if (wg && use_side_stream()) {   // head parameter gradients beside the dgrad chain; joined at the end of this call
+        FV_TRY(ensure_side_stream(p));
+        FV_CUDA(cudaEventRecord(p->ev_fork, st));
+        FV_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+        hs = p->side;
+        side_used = true;
+      }
       FV_TRY(head_bwd<AT>(b.x[c.depth], dlogits, B, S, E, p->P(FERVIT_G_HEAD_LN_W), p->P(FERVIT_G_HEAD_LN_B),
                           p->P(FERVIT_G_HEAD_W), c.C, b.head_mean, b.head_rstd, dh, b.dx[0],
-                          F32 ? nullptr : (AT*)b.dx_at[0], wg, b.scratch, G[FERVIT_G_HEAD_W], G[FERVIT_G_HEAD_LN_W],
-                          G[FERVIT_G_HEAD_LN_B], G[FERVIT_G_HEAD_B], st));
+                          F32 ? nullptr : (AT*)b.dx_at[0], wg, b.head_scratch, G[FERVIT_G_HEAD_W],
+                          G[FERVIT_G_HEAD_LN_W], G[FERVIT_G_HEAD_LN_B], G[FERVIT_G_HEAD_B], st, hs));
     } else if (stage <= c.depth) {
       const int i = c.depth - stage;
       BlockBufs& k = b.blk[i];
@@ -531,15 +553,12 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
             const Bufs::AdParts& q = b.ad[i];
             cudaStream_t ws = st;
             if (use_side_stream()) {
-              if (!p->side) {
-                FV_CUDA(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
-                FV_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-                FV_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
-              }
+              FV_TRY(ensure_side_stream(p));
               FV_CUDA(cudaEventRecord(p->ev_fork, st));
               FV_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
               ws = p->side;
               side_pending = true;
+              side_used = true;
             }
             Ctx cw = cx;
             cw.st = ws;
@@ -730,6 +749,10 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
       }
     }
+  }
+  if (side_used) {  // everything forked in this call is complete before the gradients are finalised / handed out
+    FV_CUDA(cudaEventRecord(p->ev_tail, p->side));
+    FV_CUDA(cudaStreamWaitEvent(st, p->ev_tail, 0));
   }
   if (!ad_jobs.empty()) FV_TRY(adapter_grad_finalize(ad_jobs.data(), (int)ad_jobs.size(), b.ad_fin, st));
   return 0;
