@@ -76,6 +76,8 @@ SIGNATURES = {
     "fervit_premodules_backward": (_i, [C.POINTER(PreModules), _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fervit_linear_forward": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "fervit_debug_gemm_clock": (_i, [_p, _p]),
+    "fervit_adapter_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
+    "fervit_adapter_backward_input": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "fervit_adamw_scratch_floats": (_ll, [_i, _p]),
     "fervit_adamw_step": (_i, [_i, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p]),
     "fervit_linear_dgrad": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),

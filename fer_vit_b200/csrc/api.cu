@@ -75,6 +75,23 @@ FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, co
   return gemm_bf16_tc((const bf16*)x, K, false, (const bf16*)W, K, false, M, N, K, 1, force_bn, e, S_(stream));
 }
 
+FV_API int fervit_adapter_forward(const void* x_bf16, const float* x_f32, const void* W1, const float* b1, const void* W2,
+                                  const float* b2, const float* alpha, int T, int E, void* g, void* d, float* y,
+                                  void* stream) {
+  FV_CHECK(adapter_fused_supported(T, E, 64), "adapter_forward: needs E a multiple of 256 and bottleneck 64 (T=%d E=%d)",
+           T, E);
+  return adapter_fused(0, (const bf16*)x_bf16, (const bf16*)W1, (const bf16*)W2, x_f32, b1, b2, alpha, nullptr, (bf16*)g,
+                       (bf16*)d, y, nullptr, T, E, S_(stream));
+}
+
+FV_API int fervit_adapter_backward_input(const void* dy_bf16, const float* dy_f32, const void* W2t, const void* W1t,
+                                         const float* alpha, const void* d, int T, int E, void* du, float* dx,
+                                         void* dx_bf16, void* stream) {
+  FV_CHECK(adapter_fused_supported(T, E, 64), "adapter_backward_input: needs E a multiple of 256 and bottleneck 64");
+  return adapter_fused(1, (const bf16*)dy_bf16, (const bf16*)W2t, (const bf16*)W1t, dy_f32, nullptr, nullptr, alpha,
+                       (const bf16*)d, (bf16*)du, nullptr, dx, (bf16*)dx_bf16, T, E, S_(stream));
+}
+
 FV_API long long fervit_adamw_scratch_floats(int n, const long long* numel) {
   return (n > 0 && numel) ? adamw_scratch_floats(n, numel) : 8;
 }

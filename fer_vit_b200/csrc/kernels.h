@@ -1,6 +1,7 @@
 // Internal launch wrappers implemented across the .cu files of this directory.
 #pragma once
 #include "common.cuh"
+#include <cuda.h>
 
 namespace fervit {
 
@@ -13,6 +14,13 @@ bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilog
 int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn, const Epilogue& e,
                   int kind, cudaStream_t stream);
 int gemm_tc2_clock_probe(double* ns, double* cycles);
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, uint64_t outer, uint64_t ld,
+                 uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
+// adapter_tc.cu: AdapterModule forward / input-gradient fused into one tensor-core kernel each (bf16, bottleneck 64)
+bool adapter_fused_supported(int T, int E, int A);
+int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, const float* res, const float* b1,
+                  const float* b2, const float* alpha_ptr, const bf16* d_in, bf16* s0, bf16* s1, float* out,
+                  bf16* out_bf16, int T, int E, cudaStream_t stream);
 // gemm_simt.cu
 int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, int M,
                   int N, int K, int splits, const Epilogue& epi, cudaStream_t stream);

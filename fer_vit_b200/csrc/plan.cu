@@ -450,13 +450,26 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
         e.out_f32 = x2;
         if (!F32) e.out = k.x2_at;
         FV_TRY(linear<AT>(cx, (const AT*)k.g1, T, p->bslot(i, FERVIT_B_FC2_W), false, e));
-        Epilogue d = make_epilogue();
-        d.bias = p->PB(i, FERVIT_B_AD1_B); d.act = ACT_GELU; d.out_pre = k.ua; d.pre_is_deriv = 1; d.out = k.ga; d.ldo = A;
-        FV_TRY(linear<AT>(cx, (const AT*)k.x2_at, T, p->bslot(i, FERVIT_B_AD1_W), false, d));
-        Epilogue u = make_epilogue();
-        u.bias = p->PB(i, FERVIT_B_AD2_B); u.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); u.residual = x2;
-        u.out_f32 = b.x[i + 1]; u.ldo = E;
-        FV_TRY(linear<AT>(cx, (const AT*)k.ga, T, p->bslot(i, FERVIT_B_AD2_W), false, u));
+        bool fused = false;
+        if constexpr (!F32) {
+          if (adapter_fused_supported(T, E, A)) {
+            // down-projection, GELU, up-projection, alpha and residual in one tensor-core kernel (adapter_tc.cu)
+            FV_TRY(adapter_fused(0, (const bf16*)k.x2_at, p->WB(p->bslot(i, FERVIT_B_AD1_W)),
+                                 p->WB(p->bslot(i, FERVIT_B_AD2_W)), x2, p->PB(i, FERVIT_B_AD1_B),
+                                 p->PB(i, FERVIT_B_AD2_B), p->PB(i, FERVIT_B_ALPHA), nullptr, (bf16*)k.ga, (bf16*)k.ua,
+                                 b.x[i + 1], nullptr, T, E, st));
+            fused = true;
+          }
+        }
+        if (!fused) {
+          Epilogue d = make_epilogue();
+          d.bias = p->PB(i, FERVIT_B_AD1_B); d.act = ACT_GELU; d.out_pre = k.ua; d.pre_is_deriv = 1; d.out = k.ga; d.ldo = A;
+          FV_TRY(linear<AT>(cx, (const AT*)k.x2_at, T, p->bslot(i, FERVIT_B_AD1_W), false, d));
+          Epilogue u = make_epilogue();
+          u.bias = p->PB(i, FERVIT_B_AD2_B); u.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); u.residual = x2;
+          u.out_f32 = b.x[i + 1]; u.ldo = E;
+          FV_TRY(linear<AT>(cx, (const AT*)k.ga, T, p->bslot(i, FERVIT_B_AD2_W), false, u));
+        }
       } else {
         e.out_f32 = b.x[i + 1];
         FV_TRY(linear<AT>(cx, (const AT*)k.g1, T, p->bslot(i, FERVIT_B_FC2_W), false, e));
@@ -540,10 +553,21 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       if (!post) {
         // ---- adapter ----  (AdapterModule backward, hybrid_latent_vit.py:264-265)
         if (A) {
-          // du = alpha * (dy W2) * gelu'(u): one GEMM, derivative and alpha in its epilogue
+          bool fused = false;
+          if constexpr (!F32) fused = adapter_fused_supported(T, E, A);
           Epilogue e = make_epilogue();
-          e.act_bwd = ACT_DERIV; e.aux = k.ua; e.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); e.out = b.du_ad; e.ldo = A;
-          FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_AD2_W), true, e));
+          if (fused) {
+            // du = alpha * (dy W2) * gelu'(u) and dx = dy + du W1 in one tensor-core kernel (adapter_tc.cu)
+            if constexpr (!F32)
+              FV_TRY(adapter_fused(1, (const bf16*)DXA(cur), p->WBT(p->bslot(i, FERVIT_B_AD2_W)),
+                                   p->WBT(p->bslot(i, FERVIT_B_AD1_W)), DX(cur), nullptr, nullptr,
+                                   p->PB(i, FERVIT_B_ALPHA), (const bf16*)k.ua, (bf16*)b.du_ad, nullptr, DX(cur ^ 1),
+                                   (bf16*)ATOUT(cur ^ 1), T, E, st));
+          } else {
+            // du = alpha * (dy W2) * gelu'(u): one GEMM, derivative and alpha in its epilogue
+            e.act_bwd = ACT_DERIV; e.aux = k.ua; e.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); e.out = b.du_ad; e.ldo = A;
+            FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_AD2_W), true, e));
+          }
           if (GB(i, FERVIT_B_AD2_W)) {
             FV_CHECK(GB(i, FERVIT_B_AD2_B) && GB(i, FERVIT_B_AD1_W) && GB(i, FERVIT_B_AD1_B) && GB(i, FERVIT_B_ALPHA),
                      "backward: adapter gradients must be requested together");
@@ -576,9 +600,11 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
             job.s2 = q.s2; job.s1 = q.s1; job.chunks = q.chunks; job.E = E; job.A = A;
             ad_jobs.push_back(job);
           }
-          e = make_epilogue();
-          e.residual = DX(cur); e.out_f32 = DX(cur ^ 1); e.out = ATOUT(cur ^ 1); e.ldo = E;
-          FV_TRY(linear<AT>(cx, (const AT*)b.du_ad, T, p->bslot(i, FERVIT_B_AD1_W), true, e));
+          if (!fused) {
+            e = make_epilogue();
+            e.residual = DX(cur); e.out_f32 = DX(cur ^ 1); e.out = ATOUT(cur ^ 1); e.ldo = E;
+            FV_TRY(linear<AT>(cx, (const AT*)b.du_ad, T, p->bslot(i, FERVIT_B_AD1_W), true, e));
+          }
           cur ^= 1;
         }
         // ---- MLP ----

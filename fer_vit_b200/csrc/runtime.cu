@@ -42,11 +42,19 @@ struct ProfRec { cudaEvent_t a, b; int cls; double work; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
+// Events come from a pool created when profiling is switched on: creating two events per launch on the hot host path
+// made the profiled pass host-bound, the GPU idled between launches and the idle time landed inside the intervals.
+static std::vector<cudaEvent_t> g_pool;
+static size_t g_pool_next = 0;
+constexpr size_t PROF_POOL = 8192;
+
 bool prof_enabled() { return g_prof_on; }
 int prof_open(int cls, double work, cudaStream_t st) {
+  if (g_pool_next + 2 > g_pool.size()) return -1;   // pool exhausted: stop recording rather than stall the host
   ProfRec r;
   r.cls = cls; r.work = work;
-  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+  r.a = g_pool[g_pool_next++];
+  r.b = g_pool[g_pool_next++];
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
   return (int)g_prof.size() - 1;
@@ -55,9 +63,15 @@ void prof_close(int id, cudaStream_t st) {
   if (id >= 0 && id < (int)g_prof.size()) cudaEventRecord(g_prof[id].b, st);
 }
 void prof_enable(bool on) {
-  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
-  g_prof_on = on;
+  g_pool_next = 0;
+  if (on && g_pool.empty()) {
+    g_pool.resize(PROF_POOL);
+    for (auto& e : g_pool) {
+      if (cudaEventCreate(&e) != cudaSuccess) { g_pool.clear(); break; }
+    }
+  }
+  g_prof_on = on && !g_pool.empty();
 }
 int prof_read(int cls, double* ms, double* work, long long* count) {
   double tm = 0, w = 0; long long n = 0;

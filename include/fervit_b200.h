@@ -237,6 +237,17 @@ int fervit_dropout_mask(float* out, long long n, float p, unsigned long long see
 #define FERVIT_SITE_INPUT 0xFFFF0u
 #define FERVIT_SITE_HEAD 0xFFFF1u
 
+/* AdapterModule (hybrid_latent_vit.py:249-265) fused on the tensor cores, bf16 mode, bottleneck 64, E % 256 == 0:
+ *   forward : y = x + alpha * (GELU(x W1^T + b1) W2^T + b2); saves g = GELU(u) and d = GELU'(u), both [T,64] bf16.
+ *             x_bf16 / x_f32: the same input as bf16 (MMA operand) and fp32 (residual); W1 [64,E], W2 [E,64] bf16.
+ *   backward: du = alpha * (dy W2) * d, dx = dy + du W1. W2t [64,E] and W1t [E,64] are the TRANSPOSED weights (bf16);
+ *             dx_bf16 may be NULL. Weight gradients: fervit_linear_wgrad on (dy, g) and (du, x). */
+int fervit_adapter_forward(const void* x_bf16, const float* x_f32, const void* W1, const float* b1, const void* W2,
+                           const float* b2, const float* alpha, int T, int E, void* g, void* d, float* y, void* stream);
+int fervit_adapter_backward_input(const void* dy_bf16, const float* dy_f32, const void* W2t, const void* W1t,
+                                  const float* alpha, const void* d, int T, int E, void* du, float* dx, void* dx_bf16,
+                                  void* stream);
+
 /* Fused AdamW over n fp32 tensors (device pointer tables live in HOST memory; they are passed to the kernels by
  * value): torch.optim.AdamW semantics (decoupled weight decay, bias correction, amsgrad off) with per-tensor
  * hyper-parameter groups, the step the reference trainers run right after backward

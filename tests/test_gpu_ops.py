@@ -384,3 +384,48 @@ def test_fused_adamw_matches_torch(lib, max_norm):
     errs = [relerr(b, a) for a, b in zip(ref, our)]
     record("fused_adamw", max_norm=max_norm or 0.0, err=max(errs))
     assert max(errs) < 2e-6, errs
+
+
+# ------------------------------------------------------------------------------------------------ fused adapter
+@pytest.mark.parametrize("T,E", [(128, 256), (300, 768), (4864, 768), (19 * 7, 512)])
+def test_adapter_fused_tcgen05(lib, T, E):
+    """AdapterModule forward and input-gradient as one tensor-core kernel each (adapter_tc.cu) against fp64 math on the
+    same bf16 operands (hybrid_latent_vit.py:249-265)."""
+    L = lib
+    g_ = torch.Generator(device="cuda").manual_seed(T + E)
+    rn = lambda *s: torch.randn(*s, device="cuda", generator=g_)
+    x = rn(T, E)
+    xb = x.bfloat16()
+    W1 = (rn(64, E) / math.sqrt(E)).bfloat16()
+    W2 = (rn(E, 64) / 8).bfloat16()
+    b1, b2 = 0.1 * rn(64), 0.1 * rn(E)
+    alpha = torch.tensor([0.37], device="cuda")
+    gq = torch.full((T, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dq = torch.full_like(gq, float("nan"))
+    y = torch.full((T, E), float("nan"), device="cuda")
+    L.check(L.lib().fervit_adapter_forward(xb.data_ptr(), x.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
+                                           b2.data_ptr(), alpha.data_ptr(), T, E, gq.data_ptr(), dq.data_ptr(),
+                                           y.data_ptr(), st()))
+    torch.cuda.synchronize()
+    u = xb.double() @ W1.double().t() + b1.double()
+    g_ref, d_ref = gelu(u), dgelu(u)
+    y_ref = x.double() + alpha.double() * (gq.double() @ W2.double().t() + b2.double())   # from the kernel's own bf16 g
+    e_g, e_d, e_y = relerr(gq.float(), g_ref), relerr(dq.float(), d_ref), relerr(y, y_ref)
+    assert e_g < 4e-3 and e_d < 4e-3, (e_g, e_d)
+    assert e_y < 2e-6, e_y
+    # backward: du = alpha * (dy W2) * d ; dx = dy + du W1
+    dy = rn(T, E)
+    dyb = dy.bfloat16()
+    W2t, W1t = W2.t().contiguous(), W1.t().contiguous()
+    du = torch.full((T, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    dx = torch.full((T, E), float("nan"), device="cuda")
+    dxb = torch.full((T, E), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(L.lib().fervit_adapter_backward_input(dyb.data_ptr(), dy.data_ptr(), W2t.data_ptr(), W1t.data_ptr(),
+                                                  alpha.data_ptr(), dq.data_ptr(), T, E, du.data_ptr(), dx.data_ptr(),
+                                                  dxb.data_ptr(), st()))
+    torch.cuda.synchronize()
+    du_ref = alpha.double() * (dyb.double() @ W2.double()) * dq.double()
+    dx_ref = dy.double() + du.double() @ W1.double()
+    e_du, e_dx, e_dxb = relerr(du.float(), du_ref), relerr(dx, dx_ref), relerr(dxb.float(), dx_ref)
+    record("adapter_fused", T=T, E=E, err_g=e_g, err_d=e_d, err_y=e_y, err_du=e_du, err_dx=e_dx)
+    assert e_du < 4e-3 and e_dx < 2e-6 and e_dxb < 4e-3, (e_du, e_dx, e_dxb)
