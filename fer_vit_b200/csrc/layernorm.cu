@@ -165,6 +165,74 @@ ln_bwd_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const floa
 
 static inline int chunks_for(int E) { return (E + 127) / 128; }
 
+// Streaming backward (no parameter gradients, no dropout), TWO warps per row: each warp owns half of the row's 128-column
+// chunks, the two partial sums meet in shared memory (named barrier per warp pair). ncu on the one-warp-per-row form at
+// 4864 x 768: 120 registers -> 2 CTAs/SM, 2.05 waves, long-scoreboard stalls 9 per issue, L2 throughput 16 % of peak: a
+// latency problem, not a bandwidth one. Half the per-thread state (<= 64 registers) puts 32 warps on an SM.
+template <typename DT, typename AT, int CHH>
+__global__ void __launch_bounds__(WARPS * 32, 4)
+ln_bwd_pair_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                   const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
+                   int rows, int E, float* __restrict__ dx_f32, AT* __restrict__ dx_at) {
+  __shared__ float2 red[WARPS];
+  pdl_trigger();
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int pair = warp >> 1, hw = warp & 1;
+  const int row = blockIdx.x * (WARPS / 2) + pair;
+  const bool live = row < rows;
+  float4 xv[CHH], dv[CHH], rsd[CHH];
+  float s1 = 0.f, s2 = 0.f;
+  float mu = 0.f, rs = 0.f;
+  if (live) {
+    mu = mean[row];
+    rs = rstd[row];
+#pragma unroll
+    for (int i = 0; i < CHH; ++i) {
+      const int c = lane * 4 + (hw * CHH + i) * 128;
+      if (c < E) {
+        if (dres) rsd[i] = *reinterpret_cast<const float4*>(dres + (size_t)row * E + c);
+        xv[i] = *reinterpret_cast<const float4*>(x + (size_t)row * E + c);
+        dv[i] = load4<DT>(dy + (size_t)row * E + c);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CHH; ++i) {
+      const int c = lane * 4 + (hw * CHH + i) * 128;
+      if (c < E) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);  // xhat
+        dv[i] = make_float4(dv[i].x * g.x, dv[i].y * g.y, dv[i].z * g.z, dv[i].w * g.w);                          // g * dy
+        s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
+        s2 += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
+      }
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) red[warp] = make_float2(s1, s2);
+  asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+  const float2 a = red[pair * 2], b = red[pair * 2 + 1];   // fixed order: low half first
+  s1 = (a.x + b.x) / (float)E;
+  s2 = (a.y + b.y) / (float)E;
+  if (!live) return;
+#pragma unroll
+  for (int i = 0; i < CHH; ++i) {
+    const int c = lane * 4 + (hw * CHH + i) * 128;
+    if (c < E) {
+      float4 o;
+      o.x = rs * (dv[i].x - s1 - xv[i].x * s2);
+      o.y = rs * (dv[i].y - s1 - xv[i].y * s2);
+      o.z = rs * (dv[i].z - s1 - xv[i].z * s2);
+      o.w = rs * (dv[i].w - s1 - xv[i].w * s2);
+      if (dres) { o.x += rsd[i].x; o.y += rsd[i].y; o.z += rsd[i].z; o.w += rsd[i].w; }
+      if (dx_f32) *reinterpret_cast<float4*>(dx_f32 + (size_t)row * E + c) = o;
+      if (dx_at) store4<AT>(dx_at + (size_t)row * E + c, o);
+    }
+  }
+}
+
 }  // namespace ln
 
 #define FV_LN_DISPATCH(CALL)                      \
@@ -217,6 +285,13 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
                      rstd, gamma, dres, rows, E, dx_f32, dx_at, partial, at_drop))
     FV_LN_DISPATCH(FV_LN_BWD_W);
 #undef FV_LN_BWD_W
+  } else if (!at_drop.threshold) {
+    // streaming form: two warps per row (see ln_bwd_pair_kernel)
+#define FV_LN_BWD_P(CH_)                                                                                          \
+  FV_CUDA(launch_pdl(ln::ln_bwd_pair_kernel<DT, AT, CH_ / 2>, dim3(ceil_div(rows, ln::WARPS / 2)),                \
+                     dim3(ln::WARPS * 32), 0, stream, dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at))
+    FV_LN_DISPATCH(FV_LN_BWD_P);
+#undef FV_LN_BWD_P
   } else {
 #define FV_LN_BWD(CH_)                                                                                    \
   FV_CUDA(launch_pdl(ln::ln_bwd_kernel<DT, AT, false, CH_>, dim3(ceil_div(rows, ln::WARPS)), dim3(ln::WARPS * 32), 0,   \
