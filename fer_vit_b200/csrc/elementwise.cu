@@ -232,59 +232,6 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   }
 }
 
-// ---- adapter backward glue (AdapterModule, hybrid_latent_vit.py:249-265):
-//      p = dy W2 (fp32 [T,A]); du = alpha * p * gelu'(u); rowpart[blk] = sum p*g over the CTA's elements ----
-template <typename AT>
-__global__ void __launch_bounds__(256)
-adapter_bwd_kernel(const float* __restrict__ p, const AT* __restrict__ u, const AT* __restrict__ g,
-                   const float* __restrict__ alpha_ptr, size_t n4, AT* __restrict__ du, float* __restrict__ part) {
-  __shared__ float red[8];
-  const float alpha = __ldg(alpha_ptr);
-  float s = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    const float4 pv = *reinterpret_cast<const float4*>(p + i * 4);
-    const float4 uv = load4<AT>(u + i * 4);
-    const float4 gv = load4<AT>(g + i * 4);
-    s += (pv.x * gv.x + pv.y * gv.y) + (pv.z * gv.z + pv.w * gv.w);
-    float4 o;
-    o.x = alpha * pv.x * gelu_bwd(uv.x);
-    o.y = alpha * pv.y * gelu_bwd(uv.y);
-    o.z = alpha * pv.z * gelu_bwd(uv.z);
-    o.w = alpha * pv.w * gelu_bwd(uv.w);
-    store4<AT>(du + i * 4, o);
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < 8; ++w) t += red[w];
-    part[blockIdx.x] = t;
-  }
-}
-// dalpha = sum(part) + b2 . colsum(dy);  db2 = alpha * colsum(dy)
-__global__ void adapter_finalize_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ b2,
-                                        const float* __restrict__ dy_colsum, int E, const float* __restrict__ alpha_ptr,
-                                        float* __restrict__ dalpha, float* __restrict__ db2) {
-  __shared__ float red[32];
-  const float alpha = __ldg(alpha_ptr);
-  float s = 0.f;
-  for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[i];
-  for (int c = threadIdx.x; c < E; c += blockDim.x) {
-    const float cs = dy_colsum[c];
-    s += b2[c] * cs;
-    db2[c] = alpha * cs;
-  }
-  s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    dalpha[0] = t;
-  }
-}
-
 // ---- deferred gradient finalisation of the AdapterModules (hybrid_latent_vit.py:249-265) ----
 // During a block's backward only PARTIAL sums are produced (split-K slabs of the two weight-gradient GEMMs, per-chunk
 // column sums of dy and du). Once per backward stage group, two launches finish every block of the group:
@@ -560,30 +507,6 @@ int adapter_grad_finalize(const AdapterGradJob* jobs, int n, float* scratch, cud
     FV_COUNT_LAUNCH();
     FV_LAUNCH_CHECK();
   }
-  return 0;
-}
-
-int adapter_bwd_parts(size_t n) { return ew::grid_for(n / 4, 256); }
-
-template <typename AT>
-int adapter_bwd_glue(const float* p, const AT* u, const AT* g, const float* alpha_ptr, size_t n, AT* du, float* part,
-                     cudaStream_t stream) {
-  FV_CHECK(n % 4 == 0, "adapter_bwd_glue: element count must be a multiple of 4");
-  ew::adapter_bwd_kernel<AT><<<adapter_bwd_parts(n), 256, 0, stream>>>(p, u, g, alpha_ptr, n / 4, du, part);
-  FV_COUNT_LAUNCH();
-  FV_LAUNCH_CHECK();
-  return 0;
-}
-template int adapter_bwd_glue<float>(const float*, const float*, const float*, const float*, size_t, float*, float*,
-                                     cudaStream_t);
-template int adapter_bwd_glue<bf16>(const float*, const bf16*, const bf16*, const float*, size_t, bf16*, float*,
-                                    cudaStream_t);
-
-int adapter_finalize(const float* part, int nparts, const float* b2, const float* dy_colsum, int E,
-                     const float* alpha_ptr, float* dalpha, float* db2, cudaStream_t stream) {
-  ew::adapter_finalize_kernel<<<1, 256, 0, stream>>>(part, nparts, b2, dy_colsum, E, alpha_ptr, dalpha, db2);
-  FV_COUNT_LAUNCH();
-  FV_LAUNCH_CHECK();
   return 0;
 }
 

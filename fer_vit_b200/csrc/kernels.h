@@ -73,12 +73,6 @@ struct AdapterGradJob {
 };
 int adapter_grad_finalize_scratch_floats();
 int adapter_grad_finalize(const AdapterGradJob* jobs, int n, float* scratch, cudaStream_t stream);
-int adapter_bwd_parts(size_t n);
-template <typename AT>
-int adapter_bwd_glue(const float* p, const AT* u, const AT* g, const float* alpha_ptr, size_t n, AT* du, float* part,
-                     cudaStream_t stream);
-int adapter_finalize(const float* part, int nparts, const float* b2, const float* dy_colsum, int E,
-                     const float* alpha_ptr, float* dalpha, float* db2, cudaStream_t stream);
 int dropout_mask(float* out, size_t n, Dropout drop, cudaStream_t stream);
 int fill_f32(float* out, size_t n, float v, cudaStream_t stream);
 
