@@ -26,7 +26,7 @@ constexpr int BM = 128, BK = 64, AD = 64, NC = 256, UMMA_K = 16;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = EPI_WARPS * 32 + 128;
 constexpr int W_TMA = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;
-constexpr int STAGES = 3;
+constexpr int STAGES = 7;   // phase 1 is latency-bound: bytes in flight are what counts (3 stages: 6.4 us; 7: ~3 us)
 constexpr int IN_BYTES = BM * BK * 2;    // 16 KB
 constexpr int AW_BYTES = AD * BK * 2;    // 8 KB
 constexpr int STAGE_BYTES = IN_BYTES + AW_BYTES;
@@ -35,7 +35,10 @@ constexpr int BW_BYTES = NC * AD * 2;    // 32 KB
 constexpr int XT = 32 * 32 * 4, YT = 32 * 32 * 2;
 constexpr int WARP_STAGING = 2 * XT + 2 * YT;
 constexpr int BAR_BYTES = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + BW_BYTES + EPI_WARPS * WARP_STAGING + BAR_BYTES + 1024;
+// The epilogue staging tiles ALIAS the input half of the phase-1 ring: every ring stage is free once the phase-1
+// accumulator is complete (h_full), which is when the residual tiles start to travel.
+static_assert(EPI_WARPS * WARP_STAGING <= STAGES * IN_BYTES, "staging must fit in the aliased ring region");
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + BW_BYTES + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 512;           // H at columns [0, 64), Y at [256, 512)
 static_assert(SMEM_BYTES <= 232448, "adapter kernel: shared memory");
 
@@ -62,8 +65,8 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   uint8_t* smem_aw = smem + STAGES * IN_BYTES;
   uint8_t* smem_g = smem + STAGES * STAGE_BYTES;
   uint8_t* smem_bw = smem_g + G_BYTES;
-  uint8_t* staging = smem_bw + BW_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + EPI_WARPS * WARP_STAGING);
+  uint8_t* staging = smem_in;   // aliased: valid after h_full
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bw + BW_BYTES);
   uint64_t* full_bar = bars;                 // [STAGES]
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]
   uint64_t* h_full = bars + 2 * STAGES;      // phase 1 accumulator complete
@@ -163,11 +166,11 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       mbar_expect_tx(&my_ld[j & 1], XT);
       tma_load_2d(Xs + (j & 1) * XT, &tm_res, &my_ld[j & 1], col_base + j * 32, row0);
     };
-    if (lane == 0 && rows_live) { issue_res(0); issue_res(1); }   // residual tiles travel during phases 1-3
-
     // ---------------- phase 2: G = f(H) ----------------
     mbar_wait(h_full, 0, 15);
     tc_fence_after();
+    // the ring is free now (all phase-1 MMAs have completed): the residual tiles travel during phases 2-3
+    if (lane == 0 && rows_live) { issue_res(0); issue_res(1); }
     {
       uint32_t hr[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32), hr);

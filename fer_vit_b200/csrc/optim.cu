@@ -97,17 +97,49 @@ adamw_kernel(const __grid_constant__ Batch b, const float* __restrict__ hyper, c
   float* __restrict__ g = b.g[t];
   float* __restrict__ m = b.m[t];
   float* __restrict__ v = b.v[t];
-  for (int i = threadIdx.x; i < CHUNK; i += 256) {
-    const long long k = base + i;
-    if (k >= n) break;
-    const float gk = g[k] * gs;
-    const float mk = b1 * m[k] + (1.0f - b1) * gk;
-    const float vk = b2 * v[k] + (1.0f - b2) * gk * gk;
-    m[k] = mk;
-    v[k] = vk;
+  const bool wb = write_back_grad && clip_coef;
+  auto upd = [&](float& pk, float& gk, float& mk, float& vk) {
+    gk *= gs;
+    mk = b1 * mk + (1.0f - b1) * gk;
+    vk = b2 * vk + (1.0f - b2) * gk * gk;
     const float denom = sqrtf(vk) * bc2_rsqrt + eps;
-    p[k] = p[k] * decay - step_size * (mk / denom);
-    if (write_back_grad && clip_coef) g[k] = gk;
+    pk = pk * decay - step_size * (mk / denom);
+  };
+  // 16-byte accesses, four independent vectors per thread in flight (all tensors are at least 16-byte aligned: torch
+  // allocations and 64-element-aligned slices of the flat gradient buffer)
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  if (vec) {
+#pragma unroll
+    for (int it = 0; it < CHUNK / (256 * 4); ++it) {
+      const long long k = base + (long long)(it * 256 + threadIdx.x) * 4;
+      if (k + 3 < n) {
+        float4 pp = *reinterpret_cast<float4*>(p + k), gg = *reinterpret_cast<float4*>(g + k);
+        float4 mm = *reinterpret_cast<float4*>(m + k), vv = *reinterpret_cast<float4*>(v + k);
+        upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y);
+        upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+        *reinterpret_cast<float4*>(p + k) = pp;
+        *reinterpret_cast<float4*>(m + k) = mm;
+        *reinterpret_cast<float4*>(v + k) = vv;
+        if (wb) *reinterpret_cast<float4*>(g + k) = gg;
+      } else {
+        for (long long q = k; q < n && q < k + 4; ++q) {
+          float pk = p[q], gk = g[q], mk = m[q], vk = v[q];
+          upd(pk, gk, mk, vk);
+          p[q] = pk; m[q] = mk; v[q] = vk;
+          if (wb) g[q] = gk;
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < CHUNK; i += 256) {
+      const long long k = base + i;
+      if (k >= n) break;
+      float pk = p[k], gk = g[k], mk = m[k], vk = v[k];
+      upd(pk, gk, mk, vk);
+      p[k] = pk; m[k] = mk; v[k] = vk;
+      if (wb) g[k] = gk;
+    }
   }
 }
 
