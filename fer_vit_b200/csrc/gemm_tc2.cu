@@ -63,17 +63,23 @@ struct Cfg {
   // F32: 0 = bf16 kinds; 1 = fp32 kind, deep operand pipeline; 2 = fp32 kind for K <= 128 (adapter up-projection and
   // its dgrad: one or two k-blocks): a 2-stage operand ring buys four fp32 tiles per warp, so the residual of a whole
   // output tile is in flight before the accumulator is even complete
+  //      3 = fp32 kind when every CTA pair owns at most ONE tile (the N = 768 shapes at batch 256: 57 tiles on 74
+  //      pairs): nothing runs beside the epilogue, so its staging tiles ALIAS the operand ring — the ring gets all of
+  //      shared memory (7 stages instead of 4) and the epilogue four fp32 tiles per warp, loaded once the last MMA has
+  //      completed
   static constexpr int CW = F32 ? 32 : 64;                     // epilogue chunk width (columns)
-  static constexpr int XBUF = (F32 == 2) ? 4 : 2;
+  static constexpr bool ALIAS = (F32 == 3);
+  static constexpr int XBUF = (F32 >= 2) ? 4 : 2;
   static constexpr int X_BYTES = F32 ? XBUF * XT : 0;
   static constexpr int Y_BYTES = F32 ? 2 * YT : YT2;
   static constexpr int Z_BYTES = F32 ? 0 : (FWD_ACT ? YT2 : (BWD_ACT ? 2 * YT2 : 0));
   static constexpr int WARP_STAGING = X_BYTES + Y_BYTES + Z_BYTES;
-  static constexpr int STAGING = EPI_WARPS * WARP_STAGING;
+  static constexpr int STAGING = ALIAS ? 0 : EPI_WARPS * WARP_STAGING;   // bytes of shared memory of its own
   static constexpr int BAR_BYTES = 512;
   static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - STAGING;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + 1024;  // +1024: manual alignment
+  static_assert(!ALIAS || EPI_WARPS * WARP_STAGING <= STAGES * STAGE_BYTES, "aliased staging must fit in the ring");
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers; 256 or 512 (powers of two)
   static_assert(STAGES >= (F32 == 2 ? 2 : 3), "pipeline too shallow");
   static_assert(2 * STAGES + 4 + 4 * EPI_WARPS + 1 <= BAR_BYTES / 8, "barrier area too small");
@@ -104,8 +110,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::STAGES * C::A_BYTES;
-  uint8_t* staging = smem + C::STAGES * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::STAGING);
+  uint8_t* staging = C::ALIAS ? smem : smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING);
   uint64_t* full_bar = bars;                         // [STAGES]   leader's is the live one
   uint64_t* empty_bar = bars + C::STAGES;            // [STAGES]   per CTA
   uint64_t* tmem_full = bars + 2 * C::STAGES;        // [2]        per CTA
@@ -276,13 +282,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           mbar_expect_tx(&my_ld[b], XT);
           tma_load_2d(Xs + b * XT, &tm_r, &my_ld[b], col, row0);
         };
-        if (res && lane == 0 && nch > 0) {
+        if (!C::ALIAS && res && lane == 0 && nch > 0) {
           // the residual of the first XBUF chunks travels while the MMAs of this tile are still running
           tma_store_wait_read<0>();  // tiles are updated in place: earlier stores must have drained
           for (int jj = 0; jj < nch && jj < (int)XB; ++jj) issue_load(g + jj, col0 + jj * CW);
         }
         mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
         tc_fence_after();
+        if (C::ALIAS && res && lane == 0 && nch > 0) {
+          // single-tile form: the staging tiles alias the operand ring, free now that every MMA has completed
+          for (int jj = 0; jj < nch && jj < (int)XB; ++jj) issue_load(g + jj, col0 + jj * CW);
+        }
         if (nch == 0) {
           tc_fence_before();
           __syncwarp();
@@ -647,10 +657,13 @@ int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
                   const Epilogue& e, int kind, cudaStream_t stream) {
   const bool f32 = e.out_f32 != nullptr || e.residual != nullptr;
   int bn = (force_bn == 128 || force_bn == 256) ? force_bn : (N > 128 ? 256 : 128);
+  // every CTA pair gets at most one tile: the fp32 epilogue may alias the operand ring (Cfg: F32 == 3)
+  const bool single_tile = ceil_div(M, 2 * tc2::BM) * ceil_div(N, bn) <= num_sms() / 2;
 #define FV_TC2_CASE(BN_, K_, F_) return tc2::launch<BN_, K_, F_>(A, lda, B, ldb, M, N, K, e, stream)
 #define FV_TC2_BN(BN_)                                         \
   do {                                                         \
     if (f32 && K <= 128) FV_TC2_CASE(BN_, EPK_PLAIN, 2);       \
+    if (f32 && single_tile) FV_TC2_CASE(BN_, EPK_PLAIN, 3);    \
     if (f32) FV_TC2_CASE(BN_, EPK_PLAIN, 1);                   \
     switch (kind) {                                            \
       case EPK_PLAIN: FV_TC2_CASE(BN_, EPK_PLAIN, 0);      \

@@ -169,18 +169,21 @@ static inline int chunks_for(int E) { return (E + 127) / 128; }
 // chunks, the two partial sums meet in shared memory (named barrier per warp pair). ncu on the one-warp-per-row form at
 // 4864 x 768: 120 registers -> 2 CTAs/SM, 2.05 waves, long-scoreboard stalls 9 per issue, L2 throughput 16 % of peak: a
 // latency problem, not a bandwidth one. Half the per-thread state (<= 64 registers) puts 32 warps on an SM.
+// 6 warps = 3 rows per CTA, 6 CTAs per SM: 18 rows in flight per SM, so the 4864 rows of batch 256 (32.9 per SM) take
+// two rounds; 8-warp CTAs (16 rows in flight) needed a third, nearly empty one.
+constexpr int PAIR_WARPS = 6;
 template <typename DT, typename AT, int CHH>
-__global__ void __launch_bounds__(WARPS * 32, 4)
+__global__ void __launch_bounds__(PAIR_WARPS * 32, 6)
 ln_bwd_pair_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ dres,
                    int rows, int E, float* __restrict__ dx_f32, AT* __restrict__ dx_at) {
-  __shared__ float2 red[WARPS];
+  __shared__ float2 red[PAIR_WARPS];
   pdl_trigger();
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int pair = warp >> 1, hw = warp & 1;
-  const int row = blockIdx.x * (WARPS / 2) + pair;
+  const int row = blockIdx.x * (PAIR_WARPS / 2) + pair;
   const bool live = row < rows;
   float4 xv[CHH], dv[CHH], rsd[CHH];
   float s1 = 0.f, s2 = 0.f;
@@ -288,8 +291,8 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
   } else if (!at_drop.threshold) {
     // streaming form: two warps per row (see ln_bwd_pair_kernel)
 #define FV_LN_BWD_P(CH_)                                                                                          \
-  FV_CUDA(launch_pdl(ln::ln_bwd_pair_kernel<DT, AT, CH_ / 2>, dim3(ceil_div(rows, ln::WARPS / 2)),                \
-                     dim3(ln::WARPS * 32), 0, stream, dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at))
+  FV_CUDA(launch_pdl(ln::ln_bwd_pair_kernel<DT, AT, CH_ / 2>, dim3(ceil_div(rows, ln::PAIR_WARPS / 2)),           \
+                     dim3(ln::PAIR_WARPS * 32), 0, stream, dy, x, mean, rstd, gamma, dres, rows, E, dx_f32, dx_at))
     FV_LN_DISPATCH(FV_LN_BWD_P);
 #undef FV_LN_BWD_P
   } else {
