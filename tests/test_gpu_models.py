@@ -419,3 +419,30 @@ def test_fused_optimizer_updates_reach_the_bf16_weight_cache():
     fresh = copy.deepcopy(m)
     assert torch.equal(after, fresh(x).detach()), "stale bf16 weight cache after a fused optimizer step"
     assert relerr(after, before) > 1e-3, "the optimizer steps should have moved the logits"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("size,E,heads,B", [("small", 384, 6, 5), ("tiny", 192, 3, 1)])
+def test_hybrid_small_widths_and_odd_batches_vs_oracle(precision, size, E, heads, B):
+    """The reference's default `--model_size small` (train_hybrid_latent_vit.py:393-394) and `tiny`: widths that are
+    not multiples of 256 (the adapters take the unfused two-GEMM path, N % BN != 0 tiles in every GEMM), with odd
+    batch sizes down to a single sample (T = 19 rows: every tile is mostly padding)."""
+    import fer_vit_b200 as fv
+    from oracle import baseline_models as BM
+    from oracle import reference_math as R
+    fv.set_default_precision(precision)
+    sd = BM.hybrid_state_dict(E=E, depth=12, heads=heads, seed=5)
+    for i in range(12):
+        sd[f"adapters.{i}.alpha"] = torch.ones(1) * (0.1 + 0.03 * i)
+    model = fv.create_hybrid_latent_vit(model_size=size, use_pretrained=False, freeze_transformer=True,
+                                        use_adapter=True, adapter_dim=64)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(17 + B)
+    x = torch.randn(B, 18, 512, generator=g)
+    y = torch.randint(0, 7, (B,), generator=g)
+    BM.hybrid_trainable(sd)
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, heads, True, m), sd, x, y)
+    got = step(model, x.cuda(), y.cuda())
+    _compare(f"hybrid_{size}_adapter_vs_oracle", precision, got, ref, {"B": B})
