@@ -94,11 +94,37 @@ struct Params {
   float alpha;
   int has_out, has_z, has_f32, has_res;
   int pre_is_deriv;  // forward activations: the Z tile receives act'(pre) instead of pre
+  // Tail splitting: the tiles of the last, partial round (units - full_units of them) are cut into `split` column
+  // slices of BN / split columns each, so that round costs 1 / split of a tile time (epilogue included) instead of a
+  // whole one: at batch 256 the QKV GEMM has 2.31 rounds of tiles, fc1 3.08.
+  int full_units, split, virt_units;
   int debug;  // timing experiments only (results are garbage): 1 no TMA loads, 2 no MMAs, 4 no epilogue, 8 record clocks
 };
 
 // [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
 __device__ unsigned long long g_clock_probe[4];
+
+struct TileRef { int pm, n_blk, col_off, width; };
+template <int BN>
+__device__ __forceinline__ TileRef decode_unit(const Params& p, int v) {
+  TileRef t;
+  int tile = v;
+  t.col_off = 0;
+  t.width = BN;
+  if (v >= p.full_units) {
+    const int k = (v - p.full_units) / p.split, q = (v - p.full_units) % p.split;
+    tile = p.full_units + k;
+    t.width = BN / p.split;
+    t.col_off = q * t.width;
+  }
+  // n fastest: the pairs running at one time share a band of A rows across all n-blocks, so A (the big operand:
+  // activations) streams from HBM once and the weights (<= 14 MB) stay in L2. With m fastest, A was re-read once per
+  // n-block as soon as it outgrew the 126 MB L2 (K = 3072 at batch >= 1024: TMA+MMA 143 us against 107 us of MMAs
+  // alone, profiles/).
+  t.n_blk = tile % p.n_blocks;
+  t.pm = tile / p.n_blocks;
+  return t;
+}
 
 template <int BN, int KIND, int F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -125,7 +151,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const bool leader = (rank == 0);
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int units = p.pair_m_blocks * p.n_blocks;
+  const int units = p.virt_units;   // full tiles, then the column slices of the last partial round
   const int total_kb = (p.K + BK - 1) / BK;
 
   pdl_trigger();  // the next kernel may start its own prologue while this one runs
@@ -172,14 +198,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int u = pair_id; u < units; u += num_pairs) {
-        // n fastest: the pairs running at one time share a band of A rows across all n-blocks, so A (the big
-        // operand: activations) streams from HBM once and the weights (<= 14 MB) stay in L2. With m fastest, A was
-        // re-read once per n-block as soon as it outgrew the 126 MB L2 (K = 3072 at batch >= 1024: TMA+MMA 143 us
-        // against 107 us of MMAs alone, profiles/).
-        const int n_blk = u % p.n_blocks;
-        const int pm = u / p.n_blocks;
-        const int row_a = pm * (2 * BM) + (int)rank * BM;
-        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        const TileRef t = decode_unit<BN>(p, u);
+        const int row_a = t.pm * (2 * BM) + (int)rank * BM;
+        // a column slice uses the first width / 2 rows of each CTA's B tile (the box always brings BN / 2 rows)
+        const int row_b = t.n_blk * BN + t.col_off + (int)rank * (t.width / 2);
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait_parked(&empty_bar[stage], phase ^ 1, 1);
           if (p.debug & 1) {
@@ -198,11 +220,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   } else if (warp == W_MMA) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int u = pair_id; u < units; u += num_pairs, ++it) {
+        const uint32_t idesc = make_idesc(2 * BM, decode_unit<BN>(p, u).width, false, false);
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait_parked(&tmem_empty[buf], acc_phase ^ 1, 2);
@@ -243,7 +265,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the only ones this warp may read
     const int half = ew >> 2;      // column half of the tile
     constexpr int CW = C::CW;
-    constexpr int NCH = BN / 2 / CW;
     uint8_t* wst = staging + ew * C::WARP_STAGING;
     uint8_t* Xs = wst;
     uint8_t* Ys = wst + C::X_BYTES;
@@ -256,19 +277,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     uint32_t g = 0;  // chunks processed so far: double-buffered tiles use g & 1, load-barrier parity = (g >> 1) & 1
     int it = 0;
     for (int u = pair_id; u < units; u += num_pairs, ++it) {
-      const int n_blk = u % p.n_blocks;
-      const int pm = u / p.n_blocks;
+      const TileRef t = decode_unit<BN>(p, u);
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      const int row0 = pm * (2 * BM) + (int)rank * BM + quarter * 32;
-      const int col0 = n_blk * BN + half * (BN / 2);
+      const int row0 = t.pm * (2 * BM) + (int)rank * BM + quarter * 32;
+      // chunks of this unit (a full tile or a column slice), split between the two warp halves
+      const int nct = t.width / CW;
+      const int per_half = nct > 1 ? nct / 2 : 1;
+      const int c_lo = half * per_half;                       // first chunk of this half (accumulator columns c_lo*CW..)
+      const int col0 = t.n_blk * BN + t.col_off + c_lo * CW;
       int nch = 0;
-      if (row0 < p.M && col0 < p.N) {
+      if (row0 < p.M && col0 < p.N && c_lo < nct) {
         nch = (p.N - col0 + CW - 1) / CW;
-        if (nch > NCH) nch = NCH;
+        if (nch > per_half) nch = per_half;
+        if (nch > nct - c_lo) nch = nct - c_lo;
       }
       if (p.debug & 4) nch = 0;
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + half * (BN / 2));
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c_lo * CW);
 
       if constexpr (F32) {
         // ------------------------------------------------------------------------------------------------
@@ -594,6 +619,21 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   p.has_res = e.residual != nullptr;
   p.pre_is_deriv = e.pre_is_deriv;
   {
+    const int units = p.pair_m_blocks * p.n_blocks, max_pairs = num_sms() / 2;
+    p.full_units = units / max_pairs * max_pairs;
+    const int rest = units - p.full_units;
+    p.split = 1;
+    static int no_split = -1;
+    if (no_split < 0) { const char* s = getenv("FERVIT_GEMM_NO_TAIL_SPLIT"); no_split = (s && atoi(s)) ? 1 : 0; }
+    // only when complete rounds exist (otherwise there is no round to shorten) and the slices fit in one round
+    if (!no_split && p.full_units > 0 && rest > 0) {
+      const int min_w = 64;   // one 64-column chunk (bf16 kinds) / two 32-column chunks (fp32 kinds)
+      if (rest * 4 <= max_pairs && BN / 4 >= min_w) p.split = 4;
+      else if (rest * 2 <= max_pairs && BN / 2 >= min_w) p.split = 2;
+    }
+    p.virt_units = p.full_units + rest * p.split;
+  }
+  {
     static int dbg = -1;
     if (dbg != 0) { const char* s = getenv("FERVIT_GEMM_DEBUG"); dbg = s ? (atoi(s) | (1 << 30)) : 0; }
     p.debug = dbg & ~(1 << 30);
@@ -611,7 +651,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
                                  C::SMEM_BYTES));
     attr_set = true;
   }
-  const int units = p.pair_m_blocks * p.n_blocks;
+  const int units = p.virt_units;
   const int max_pairs = num_sms() / 2;
   const int pairs = units < max_pairs ? units : max_pairs;
   ProfScope prof(0, 2.0 * M * (double)N * K, stream);
