@@ -8,7 +8,7 @@ declare -A G
 G[ops_basic]="tests/test_gpu_ops.py -k 'simt or layernorm or attention or cross_entropy or premodules or adamw'"
 G[ops_tc]="tests/test_gpu_ops.py -k 'tcgen05'"
 G[ops_wgrad]="tests/test_gpu_ops.py -k 'wgrad'"
-G[models_fp32]="tests/test_gpu_models.py -k 'fp32 or fallback or roundtrip or graphed or fused'"
+G[models_fp32]="tests/test_gpu_models.py -k 'fp32 or fallback or roundtrip or (graphed and not dropout) or fused'"
 G[models_bf16]="tests/test_gpu_models.py -k 'bf16'"
 groups="$@"
 [ -z "$groups" ] && groups="ops_basic ops_tc ops_wgrad models_fp32 models_bf16"

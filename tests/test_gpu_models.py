@@ -446,3 +446,29 @@ def test_hybrid_small_widths_and_odd_batches_vs_oracle(precision, size, E, heads
     ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, heads, True, m), sd, x, y)
     got = step(model, x.cuda(), y.cuda())
     _compare(f"hybrid_{size}_adapter_vs_oracle", precision, got, ref, {"B": B})
+
+
+@pytest.mark.gpu
+def test_graphed_step_with_dropout_bf16():
+    """LatentViT in train mode (dropout 0.1 at every site) under GraphedTrainStep: the dropout masks come from the
+    counter-based hash with the device-side seed counter incremented INSIDE the graph, so every replay draws fresh
+    masks (two replays on the same batch with a zero learning rate give different losses) and training on a fixed
+    batch still converges."""
+    import fer_vit_b200 as fv
+    fv.set_default_precision("bf16")
+    torch.manual_seed(3)
+    model = fv.LatentViT(latent_dim=512, seq_len=18, embed_dim=256, depth=2, heads=4, mlp_dim=512, num_classes=7,
+                         dropout=0.1).cuda().train()
+    x = torch.randn(64, 18, 512, device="cuda")
+    y = torch.randint(0, 7, (64,), device="cuda")
+    opt = fv.FusedAdamW(model.parameters(), lr=0.0, weight_decay=0.0)
+    stepper = fv.GraphedTrainStep(model, opt, x, y)
+    l1 = float(stepper(x, y))
+    l2 = float(stepper(x, y))
+    assert l1 != l2 and abs(l1 - l2) < 0.5, (l1, l2)     # same weights (lr = 0), fresh masks
+    for g in opt.param_groups:
+        g["lr"] = 2e-3
+    opt.refresh_hyper()
+    losses = [float(stepper(x, y)) for _ in range(30)]
+    assert all(map(lambda v: v == v and v < 1e3, losses))
+    assert sum(losses[-5:]) / 5 < sum(losses[:5]) / 5 - 0.05, (losses[:5], losses[-5:])
