@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "
                                                             "the captured CUDA graph of the step")
+    ap.add_argument("--no-scaling-ref", action="store_true", help="skip the batch-4096 single-GPU reference run at N = 1")
     ap.add_argument("--watchdog", type=int, default=0, help="dump every thread's Python stack to stderr after this "
                                                              "many seconds and exit (diagnosing multi-GPU hangs)")
     args = ap.parse_args()
@@ -338,6 +339,33 @@ def main():
             hbm["layernorm"] = {"achieved_gbs": l_bytes / (l_ms * 1e-3) / 1e9, "frac": l_bytes / (l_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                                 "ms_per_step": l_ms / psteps, "launches_per_step": l_n // psteps}
 
+    # ---------------- strong-scaling denominator (N = 1 only): config 5's global batch 4096 on this one GPU ----------------
+    # The N > 1 runs of this script are BASELINE config 5 (global batch 4096 split over the GPUs: strong scaling); the
+    # N = 1 default is config 3 (batch 256). The like-for-like denominator of the 2/4/8-GPU values is therefore this
+    # number, not `value`.
+    scaling_ref = None
+    if rank == 0 and n_gpus == 1 and not args.batch and not args.no_scaling_ref:
+        Bs = 4096
+        gx = torch.randn(2, Bs, 18, 512, device=dev)
+        gy = torch.randint(0, 7, (2, Bs), device=dev)
+        big = eager_step if args.no_graph else fv.GraphedTrainStep(model, opt, gx[0], gy[0])
+        for i in range(3):
+            big(gx[i % 2], gy[i % 2])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        ks = 10
+        for i in range(ks):
+            big(gx[i % 2], gy[i % 2])
+        e1.record()
+        torch.cuda.synchronize()
+        ms_s = e0.elapsed_time(e1) / ks
+        scaling_ref = {"global_batch": Bs, "n_gpus": 1, "value": Bs / (ms_s * 1e-3), "unit": "samples/s",
+                       "ms_per_step": ms_s, "steps": ks,
+                       "note": "BASELINE config 5 on one GPU: the denominator for the strong-scaling efficiency of the "
+                               "2/4/8-GPU runs of this script (their global batch is 4096 too)"}
+        del big, gx, gy
+
     # ---------------- CPU baseline (oracle port on this box's host cores; rank 0, N = 1 only) ----------------
     cpu = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -376,6 +404,7 @@ def main():
             "roofline": roof,
             "hbm_kernels": hbm,
             "cpu_baseline": cpu,
+            "strong_scaling_ref_1gpu": scaling_ref,
         }
         if bucketer is not None:
             line["allreduce"] = {"bytes_per_step": bucketer.bytes_reduced // max(1, bucketer.calls) * args.buckets,
