@@ -698,7 +698,9 @@ int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   const bool f32 = e.out_f32 != nullptr || e.residual != nullptr;
   int bn = (force_bn == 128 || force_bn == 256) ? force_bn : (N > 128 ? 256 : 128);
   // every CTA pair gets at most one tile: the fp32 epilogue may alias the operand ring (Cfg: F32 == 3)
-  const bool single_tile = ceil_div(M, 2 * tc2::BM) * ceil_div(N, bn) <= num_sms() / 2;
+  static int no_alias = -1;
+  if (no_alias < 0) { const char* s = getenv("FERVIT_GEMM_NO_ALIAS"); no_alias = (s && atoi(s)) ? 1 : 0; }
+  const bool single_tile = !no_alias && ceil_div(M, 2 * tc2::BM) * ceil_div(N, bn) <= num_sms() / 2;
 #define FV_TC2_CASE(BN_, K_, F_) return tc2::launch<BN_, K_, F_>(A, lda, B, ldb, M, N, K, e, stream)
 #define FV_TC2_BN(BN_)                                         \
   do {                                                         \
