@@ -280,6 +280,8 @@ int attention_fwd(const AT* qkv, AT* out, float* lse, int B, int S, int H, int H
   if constexpr (std::is_same<AT, bf16>::value) {
     // S <= 32: warp-per-head tensor-core kernel (attention_tc.cu); longer sequences use the kernel below
     if (attention_tc_supported(S, HD)) return attention_tc_fwd(qkv, out, lse, B, S, H, HD, drop, stream);
+    // 32 < S <= 256: CTA-per-head tensor-core kernel (attention_tc_long.cu)
+    if (attention_tc_long_supported(S, HD)) return attention_tc_long_fwd(qkv, out, lse, B, S, H, HD, drop, stream);
   }
   if (HD == 64) return attention_fwd_t<AT, 64>(qkv, out, lse, B, S, H, drop, stream);
   if (HD == 48) return attention_fwd_t<AT, 48>(qkv, out, lse, B, S, H, drop, stream);
@@ -291,6 +293,8 @@ int attention_bwd(const AT* qkv, const AT* out, const AT* dout, const float* lse
                   int HD, Dropout drop, cudaStream_t stream) {
   if constexpr (std::is_same<AT, bf16>::value) {
     if (attention_tc_supported(S, HD)) return attention_tc_bwd(qkv, out, dout, lse, dqkv, B, S, H, HD, drop, stream);
+    if (attention_tc_long_supported(S, HD))
+      return attention_tc_long_bwd(qkv, out, dout, lse, dqkv, B, S, H, HD, drop, stream);
   }
   if (HD == 64) return attention_bwd_t<AT, 64>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);
   if (HD == 48) return attention_bwd_t<AT, 48>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);

@@ -10,6 +10,7 @@
 // qkv layout: [B*S, 3E], columns [Q | K | V], head h at columns h*HD (timm qkv / torch in_proj packing).
 #include "common.cuh"
 #include "kernels.h"
+#include "attn_frag.cuh"
 
 namespace fervit {
 
@@ -19,44 +20,8 @@ constexpr int HEADS = 4;            // (sample, head) problems per CTA
 constexpr int WARPS = 2 * HEADS;    // two warps per problem: one per 16-row tile of queries (phase 1) / keys (phase 2)
 constexpr int SP = 32;  // padded sequence
 
-template <int HD> struct Lay { static constexpr int LD = HD + 8; };  // row stride (elements): conflict-free ldmatrix
+using namespace attn_frag;
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const bf16* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_addr(p)));
-}
-// A fragment of rows [mt*16, +16), k in [ks*16, +16) of a row-major smem matrix M[row][k]
-template <int LD>
-__device__ __forceinline__ void lda(uint32_t (&a)[4], const bf16* M, int mt, int ks, int lane) {
-  ldsm_x4(a, M + (mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + ks * 16 + (lane >> 4) * 8);
-}
-// B fragments of TWO n-tiles (n in [np*16, +16)), k in [ks*16, +16), from M[n][k] (k contiguous): r[0..1] tile 2np, r[2..3] tile 2np+1
-template <int LD>
-__device__ __forceinline__ void ldb(uint32_t (&r)[4], const bf16* M, int np, int ks, int lane) {
-  ldsm_x4(r, M + (np * 16 + (lane & 7) + (lane >> 4) * 8) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
-}
-// B fragments of TWO n-tiles from M[k][n] (n contiguous): k in [kk*16, +16), n in [np*16, +16)
-template <int LD>
-__device__ __forceinline__ void ldbt(uint32_t (&r)[4], const bf16* M, int np, int kk, int lane) {
-  ldsm_x4_t(r, M + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + np * 16 + (lane >> 4) * 8);
-}
-// A fragment of the TRANSPOSE: rows m in [mt*16, +16), k in [kk*16, +16), from a matrix stored as M[k][m] (m contiguous)
-template <int LD>
-__device__ __forceinline__ void lda_t(uint32_t (&a)[4], const bf16* M, int mt, int kk, int lane) {
-  ldsm_x4_t(a, M + (kk * 16 + (lane & 7) + ((lane >> 4) & 1) * 8) * LD + mt * 16 + ((lane >> 3) & 1) * 8);
-}
 // stage M[S][HD] (global, row stride rs) into smem [32][LD], zero-filling rows S..31. Asynchronous 16-byte copies
 // (cp.async, L2 -> smem without a register round trip): all ~5 copies per lane and matrix are in flight at once, where
 // a load-then-store loop exposed one global-memory latency per unrolled pair. Caller: stage_wait() before reading.

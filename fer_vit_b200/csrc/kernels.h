@@ -95,6 +95,13 @@ int attention_tc_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H
 int attention_tc_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S,
                      int H, int HD, Dropout drop, cudaStream_t stream);
 
+// attention_tc_long.cu (bf16, 32 < S <= 256)
+bool attention_tc_long_supported(int S, int HD);
+int attention_tc_long_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, int HD, Dropout drop,
+                          cudaStream_t stream);
+int attention_tc_long_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B,
+                          int S, int H, int HD, Dropout drop, cudaStream_t stream);
+
 // head_ce.cu
 int head_fwd(const float* x, int B, int S, int E, const float* gamma, const float* beta, float eps, const float* W,
              const float* bias, int C, Dropout drop, float* logits, float* mean, float* rstd, cudaStream_t stream);

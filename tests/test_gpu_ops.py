@@ -247,10 +247,13 @@ def attn_ref(qkv, B, S, H, hd, mask=None):
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("B,S,H,hd,pdrop", [(5, 19, 2, 32, 0.0), (33, 19, 12, 64, 0.0), (3, 37, 6, 64, 0.0),
                                             (2, 197, 8, 64, 0.0), (2, 197, 8, 48, 0.0), (4, 19, 8, 64, 0.1),
-                                            (2, 5, 2, 32, 0.1)])
+                                            (2, 5, 2, 32, 0.1), (2, 197, 4, 64, 0.1), (3, 100, 2, 32, 0.1),
+                                            (2, 256, 2, 64, 0.0), (1, 33, 3, 48, 0.0), (2, 130, 2, 64, 0.1)])
 def test_attention(lib, dtype_name, B, S, H, hd, pdrop):
     L = lib
     dtype = L.F32 if dtype_name == "fp32" else L.BF16
+    if dtype == L.F32 and S > 197:
+        pytest.skip("the fp32 (CUDA-core) kernel keeps a whole head in shared memory: S <= 197 at head dim 64")
     tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
     E = H * hd
     g = torch.Generator(device="cuda").manual_seed(B + S + H + hd)
