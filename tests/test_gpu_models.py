@@ -388,7 +388,7 @@ def test_graphed_train_step_matches_eager():
         l1 = fv.cross_entropy(m1(x), y)
         l1.backward()
         o1.step()
-        losses1.append(float(l1))
+        losses1.append(float(l1.detach()))
         losses2.append(float(stepper(x, y)))
     torch.cuda.synchronize()
     assert stepper.launches_per_replay > 50
