@@ -95,8 +95,10 @@ def main():
     for name, M, N, K, kw in [("fc1+gelu", 4864, 3072, 768, dict(act=2, bias=True)),
                               ("proj+res_f32", 4864, 768, 768, dict(bias=True, residual=True, out_f32=True)),
                               ("fc2+res_f32", 4864, 768, 3072, dict(bias=True, residual=True, out_f32=True))]:
-        t = time_gemm(M, N, K, 0, a.iters, flush=flush, **kw)
-        print(json.dumps({"gemm": name, "us": round(t * 1e6, 1), "tflops": round(2 * M * N * K / t / 1e12, 1)}), flush=True)
+        for bn in sorted({0, *[int(v) for v in a.bn.split(",") if int(v) >= 0]}):
+            t = time_gemm(M, N, K, bn, a.iters, flush=flush, **kw)
+            print(json.dumps({"gemm": name, "bn": bn, "us": round(t * 1e6, 1),
+                              "tflops": round(2 * M * N * K / t / 1e12, 1)}), flush=True)
 
 
 if __name__ == "__main__":
