@@ -49,6 +49,11 @@ class PreModules(C.Structure):
     ]
 
 
+class LatentAugmentParams(C.Structure):
+    _fields_ = [("noise_std", C.c_float), ("use_scale", C.c_int), ("scale_min", C.c_float),
+                ("scale_max", C.c_float), ("mask_prob", C.c_float)]
+
+
 _p, _i, _ll, _f, _u64, _u32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_uint
 
 # name -> (restype, argtypes); every symbol include/fervit_b200.h declares
@@ -71,6 +76,9 @@ SIGNATURES = {
     "fervit_plan_num_stages": (_i, [_p]),
     "fervit_plan_backward": (_i, [_p, _p, _i, _p, _ll, _i, _u64, _p, _p, C.POINTER(_p), _i, _i, _i, _p]),
     "fervit_cross_entropy": (_i, [_p, _p, _p, _f, _i, _i, _p, _f, _p, _p, _p, _p]),
+    "fervit_cross_entropy_mixup": (_i, [_p, _p, _p, _p, _f, _i, _i, _f, _p, _f, _p, _p, _p]),
+    "fervit_latent_batch": (_i, [_p, _p, _ll, _p, _i, _ll, C.POINTER(LatentAugmentParams), _u64, _p, _p, C.c_double, _p, _p,
+                                _p, _p, _p]),
     "fervit_premodules_forward": (_i, [C.POINTER(PreModules), _p, _i, _i, _i, _p, _p]),
     "fervit_premodules_scratch_floats": (_ll, [_i, _i, _i]),
     "fervit_premodules_backward": (_i, [C.POINTER(PreModules), _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

@@ -32,6 +32,31 @@ FV_API int fervit_cross_entropy(const float* logits, const long long* labels, co
                        S_(stream));
 }
 
+FV_API int fervit_cross_entropy_mixup(const float* logits, const long long* labels, const long long* mix_index,
+                                      const float* weight, float label_smoothing, int B, int C, float lam,
+                                      const float* lam_dev, float grad_scale, float* loss, float* dlogits,
+                                      void* stream) {
+  FV_CHECK(logits && labels && mix_index && loss, "cross_entropy_mixup: null argument");
+  return cross_entropy_mixup(logits, labels, mix_index, weight, label_smoothing, B, C, lam, lam_dev, grad_scale, loss,
+                             dlogits, S_(stream));
+}
+
+FV_API int fervit_latent_batch(const float* latents, const long long* labels, long long n_rows,
+                               const long long* sample_idx, int B, long long row_elems,
+                               const fervit_latent_augment* aug, unsigned long long seed,
+                               const unsigned long long* seed_dev, const long long* mix_index, double lam,
+                               const float* lam_dev, float* out, long long* labels_out, int* status, void* stream) {
+  FV_CHECK(latents && out, "latent_batch: null argument");
+  FV_CHECK(n_rows >= 1, "latent_batch: empty latent table");
+  FV_CHECK(sample_idx || B <= n_rows, "latent_batch: batch larger than the latent table and no sample_idx");
+  FV_CHECK(!labels_out || labels, "latent_batch: labels_out needs labels");
+  FV_CHECK(!mix_index || lam_dev || (lam >= 0.0 && lam <= 1.0), "latent_batch: lam must be in [0, 1] (got %g)", lam);
+  return latent_batch(latents, labels, n_rows, sample_idx, B, row_elems, aug ? aug->noise_std : 0.f,
+                      aug ? aug->use_scale : 0, aug ? aug->scale_min : 1.f, aug ? aug->scale_max : 1.f,
+                      aug ? aug->mask_prob : 0.f, seed, seed_dev, mix_index, lam, lam_dev, out, labels_out, status,
+                      S_(stream));
+}
+
 static PreParams to_pre(const fervit_premodules* p) {
   PreParams q;
   q.use_spe = p->use_spe; q.use_lwn = p->use_lwn; q.use_res = p->use_lwn_res; q.use_leam = p->use_leam;

@@ -198,12 +198,14 @@ __device__ __forceinline__ float act_bwd(int act, float pre) {
 // Counter-based dropout: keep(seed, site, idx) is a pure function, so backward recomputes the
 // mask instead of storing it, and tests can materialise the very same mask for the oracle.
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+__host__ __device__ __forceinline__ uint64_t mix_hash64(uint64_t seed, uint32_t site, uint64_t idx) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(site + 1) + idx * 0xD1B54A32D192ED03ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z = z ^ (z >> 31);
-  return (uint32_t)(z >> 32);
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+  return (uint32_t)(mix_hash64(seed, site, idx) >> 32);
 }
 // threshold = round(p * 2^32); keep iff hash >= threshold
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx,

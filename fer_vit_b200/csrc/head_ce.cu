@@ -293,6 +293,97 @@ ce_kernel(const float* __restrict__ logits, const long long* __restrict__ labels
   }
 }
 
+
+// Mixup loss of the LatentViT trainers (train_latent_vit.py:131):
+//   loss = lam * CE(z, y) + (1 - lam) * CE(z, y[index]), each term with its own denominator sum_i w[label_i];
+// one launch, one pass over the logits: per row the two target distributions are merged as
+//   t[i,c] = lam * ta[i,c] / den_a + (1 - lam) * tb[i,c] / den_b,  loss = sum_i sum_c t[i,c] (lse_i - z[i,c]),
+//   dlogits[i,c] = softmax[i,c] * sum_c t[i,c] - t[i,c].
+__global__ void __launch_bounds__(256)
+ce_mixup_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                const long long* __restrict__ index, const float* __restrict__ weight, float smoothing, int B, int C,
+                float lam_host, const float* __restrict__ lam_dev, float grad_scale, float* __restrict__ loss_out,
+                float* __restrict__ dlogits) {
+  __shared__ float red[2][8];
+  __shared__ float s_den[2];
+  const int tid = threadIdx.x;
+  const float lam = lam_dev ? lam_dev[0] : lam_host;
+  float pa = 0.f, pb = 0.f;
+  for (int i = tid; i < B; i += blockDim.x) {
+    pa += weight ? weight[labels[i]] : 1.0f;
+    pb += weight ? weight[labels[index[i]]] : 1.0f;
+  }
+  pa = warp_sum(pa);
+  pb = warp_sum(pb);
+  if ((tid & 31) == 0) {
+    red[0][tid >> 5] = pa;
+    red[1][tid >> 5] = pb;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[tid][w];
+    s_den[tid] = t;
+  }
+  __syncthreads();
+  const float ka = lam / s_den[0], kb = (1.0f - lam) / s_den[1];
+  float lsum = 0.f;
+  for (int i = tid; i < B; i += blockDim.x) {
+    const float* z = logits + (size_t)i * C;
+    float zl[MAXC];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      zl[c] = (c < C) ? z[c] : -INFINITY;
+      mx = fmaxf(mx, zl[c]);
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < C) se += expf(zl[c] - mx);
+    const float lse = mx + logf(se);
+    const int ya = (int)labels[i], yb = (int)labels[index[i]];
+    const float wa = weight ? weight[ya] : 1.0f, wb = weight ? weight[yb] : 1.0f;
+    float li = 0.f, tsum = 0.f;
+    float t[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {
+        const float wc = weight ? weight[c] : 1.0f;
+        const float sm = (smoothing / (float)C) * wc;
+        t[c] = ka * ((c == ya ? (1.0f - smoothing) * wa : 0.f) + sm) +
+               kb * ((c == yb ? (1.0f - smoothing) * wb : 0.f) + sm);
+        li += t[c] * (lse - zl[c]);
+        tsum += t[c];
+      }
+    }
+    lsum += li;
+    if (dlogits) {
+      // the row of dlogits sums to zero exactly; the heavier target class takes minus the sum of the others
+      const int ypiv = (lam >= 0.5f) ? ya : yb;
+      float others = 0.f;
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        if (c < C && c != ypiv) {
+          const float d = grad_scale * (expf(zl[c] - lse) * tsum - t[c]);
+          dlogits[(size_t)i * C + c] = d;
+          others += d;
+        }
+      }
+      dlogits[(size_t)i * C + ypiv] = -others;
+    }
+  }
+  lsum = warp_sum(lsum);
+  __syncthreads();
+  if ((tid & 31) == 0) red[0][tid >> 5] = lsum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[0][w];
+    loss_out[0] = t;
+  }
+}
+
 }  // namespace head
 
 int head_fwd(const float* x, int B, int S, int E, const float* gamma, const float* beta, float eps, const float* W,
@@ -352,6 +443,19 @@ int cross_entropy(const float* logits, const long long* labels, const float* wei
   FV_CHECK(B >= 1, "cross_entropy: empty batch");
   head::ce_kernel<<<1, 256, 0, stream>>>(logits, labels, weight, smoothing, B, C, den_in, grad_scale, loss, dlogits,
                                          den_out);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+
+int cross_entropy_mixup(const float* logits, const long long* labels, const long long* index, const float* weight,
+                        float smoothing, int B, int C, float lam, const float* lam_dev, float grad_scale, float* loss,
+                        float* dlogits, cudaStream_t stream) {
+  FV_CHECK(C >= 1 && C <= head::MAXC, "cross_entropy_mixup: num_classes must be in [1, %d] (got %d)", head::MAXC, C);
+  FV_CHECK(B >= 1, "cross_entropy_mixup: empty batch");
+  FV_CHECK(lam_dev || (lam >= 0.f && lam <= 1.f), "cross_entropy_mixup: lam must be in [0, 1] (got %g)", (double)lam);
+  head::ce_mixup_kernel<<<1, 256, 0, stream>>>(logits, labels, index, weight, smoothing, B, C, lam, lam_dev,
+                                               grad_scale, loss, dlogits);
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

@@ -114,6 +114,15 @@ int head_bwd(const float* x, const float* dlogits, int B, int S, int E, const fl
 int cross_entropy(const float* logits, const long long* labels, const float* weight, float smoothing, int B, int C,
                   const float* den_in, float grad_scale, float* loss, float* dlogits, float* den_out,
                   cudaStream_t stream);
+int cross_entropy_mixup(const float* logits, const long long* labels, const long long* index, const float* weight,
+                        float smoothing, int B, int C, float lam, const float* lam_dev, float grad_scale, float* loss,
+                        float* dlogits, cudaStream_t stream);
+
+// latent_batch.cu
+int latent_batch(const float* latents, const long long* labels, long long n_rows, const long long* sample_idx, int B,
+                 long long row, float noise_std, int use_scale, float scale_min, float scale_max, float mask_prob,
+                 uint64_t seed, const unsigned long long* seed_dev, const long long* mix_index, double lam,
+                 const float* lam_dev, float* out, long long* labels_out, int* status, cudaStream_t stream);
 
 // premodules.cu
 namespace pre {

@@ -267,6 +267,47 @@ def cross_entropy(logits, labels, weight=None, label_smoothing: float = 0.0, den
     return _CrossEntropyFunction.apply(logits, labels, weight, label_smoothing, den)
 
 
+class _MixupCrossEntropyFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, index, lam, weight, label_smoothing):
+        _require_cuda(logits, "logits")
+        lg = logits.contiguous().float()
+        lb = labels.contiguous().long()
+        ix = index.contiguous().long()
+        if not lb.is_cuda or not ix.is_cuda:
+            raise RuntimeError("fer_vit_b200: mixup_cross_entropy needs labels and index on the CUDA device")
+        B, Cn = lg.shape
+        if lb.numel() != B or ix.numel() != B:
+            raise RuntimeError("fer_vit_b200: mixup_cross_entropy: labels and index must have one entry per row")
+        lam_dev = lam if isinstance(lam, torch.Tensor) else None
+        if lam_dev is not None and (not lam_dev.is_cuda or lam_dev.dtype != torch.float32 or lam_dev.numel() != 1):
+            raise RuntimeError("fer_vit_b200: a tensor lam must be one float32 element on the CUDA device")
+        loss = torch.empty((), dtype=torch.float32, device=lg.device)
+        need = logits.requires_grad
+        dl = torch.empty_like(lg) if need else None
+        w = weight.contiguous().float() if weight is not None else None
+        L.check(L.lib().fervit_cross_entropy_mixup(
+            lg.data_ptr(), lb.data_ptr(), ix.data_ptr(), w.data_ptr() if w is not None else None,
+            float(label_smoothing), B, Cn, 0.0 if lam_dev is not None else float(lam),
+            lam_dev.data_ptr() if lam_dev is not None else None, 1.0, loss.data_ptr(),
+            dl.data_ptr() if need else None, _stream_ptr()))
+        if need:
+            ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g, None, None, None, None, None
+
+
+def mixup_cross_entropy(logits, labels, index, lam, weight=None, label_smoothing: float = 0.0):
+    """``lam * criterion(logits, labels) + (1 - lam) * criterion(logits, labels[index])`` of the LatentViT trainers
+    (train_latent_vit.py:131) in one kernel. ``lam``: python float, or a one-element float32 CUDA tensor (read on the
+    device, so a captured CUDA graph can change it between replays)."""
+    return _MixupCrossEntropyFunction.apply(logits, labels, index, lam, weight, label_smoothing)
+
+
 class CrossEntropyLoss(torch.nn.Module):
     """Drop-in for nn.CrossEntropyLoss(weight=?, label_smoothing=?) as the reference trainers build it
     (train_hybrid_latent_vit.py:236-241, train_latent_vit.py:248-253), computed by the native kernel."""
@@ -278,3 +319,7 @@ class CrossEntropyLoss(torch.nn.Module):
 
     def forward(self, logits, labels, den=None):
         return cross_entropy(logits, labels, self.weight, self.label_smoothing, den)
+
+    def mixup(self, logits, labels, index, lam):
+        """lam * self(logits, labels) + (1 - lam) * self(logits, labels[index]), fused (train_latent_vit.py:131)."""
+        return mixup_cross_entropy(logits, labels, index, lam, self.weight, self.label_smoothing)

@@ -167,6 +167,46 @@ int fervit_cross_entropy(const float* logits, const long long* labels, const flo
                          float* den_out, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * Mixup loss of the LatentViT trainers (train_latent_vit.py:131, train_latent_vit_v2.py the same expression):
+ *   loss = lam * CE(z, labels) + (1 - lam) * CE(z, labels[mix_index]),  CE as fervit_cross_entropy (each term divides
+ * by its own sum_i w[label_i]). One launch; dlogits may be NULL. lam_dev (device scalar, may be NULL) overrides lam,
+ * so a captured CUDA graph can draw a new lam per replay.
+ * -------------------------------------------------------------------------------------------- */
+int fervit_cross_entropy_mixup(const float* logits, const long long* labels, const long long* mix_index,
+                               const float* weight, float label_smoothing, int B, int C, float lam,
+                               const float* lam_dev, float grad_scale, float* loss, float* dlogits, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
+ * Latent batch producer: gather -> LatentAugment -> mixup in one launch over a packed latent table in HBM.
+ * Replaces, for latents already on the device, LatentFERDataset.__getitem__ + LatentAugment.__call__
+ * (data/latent_dataset.py:93-116, 28-49), the DataLoader's stacking and the mixup blend
+ * `lam * latents + (1 - lam) * latents[index]` (train_latent_vit.py:119-127).
+ *   a[b]   = keep(b) * scale(b) * (latents[sample_idx[b]] + noise_std * normal(b))   (order as the reference)
+ *   out[b] = lam * a[b] + (1 - lam) * a[mix_index[b]]                               (mix_index NULL: out = a)
+ * latents [n_rows, row_elems] fp32; sample_idx [B] (NULL: rows 0..B-1); labels [n_rows] -> labels_out [B] (both may
+ * be NULL); aug NULL = no augmentation. status (device int, may be NULL) is set to 1 if an index is out of range (the
+ * row is then read from row 0 / not mixed). out must not alias latents.
+ * Draws are counter-based, a pure function of (s = seed + *seed_dev, batch position b, element e), so a test can
+ * replay them on the host. With h64(site, i) = the 64-bit mix of csrc/common.cuh:mix_hash64(s, site, i),
+ * u(x) = (x + 0.5) / 2^32 and g = b * row_elems + e:
+ *   normal pair (g even, g + 1): z = h64(0x4C410000, g / 2), r = sqrt(-2 ln u(z >> 32)),
+ *                                t = 2 pi (u(z & 0xffffffff) - 1/2), normal(g) = r cos t, normal(g + 1) = r sin t
+ *   scale(b) = scale_min + (scale_max - scale_min) * u(h64(0x4C410002, b) >> 32)
+ *   keep(g)  = ((h64(0x4C410003, g / 4) >> 16 (g mod 4)) & 0xffff) >= max(1, floor(mask_prob * 2^16))
+ * lam is a double because the reference's `(1 - lam)` is evaluated in double before the tensor multiply rounds it.
+ * -------------------------------------------------------------------------------------------- */
+typedef struct fervit_latent_augment {
+  float noise_std;            /* 0 disables */
+  int use_scale;              /* scale_range is not None */
+  float scale_min, scale_max; /* one uniform factor per sample */
+  float mask_prob;            /* 0 disables; element kept with probability 1 - mask_prob */
+} fervit_latent_augment;
+int fervit_latent_batch(const float* latents, const long long* labels, long long n_rows, const long long* sample_idx,
+                        int B, long long row_elems, const fervit_latent_augment* aug, unsigned long long seed,
+                        const unsigned long long* seed_dev, const long long* mix_index, double lam,
+                        const float* lam_dev, float* out, long long* labels_out, int* status, void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Stand-alone pre-modules (modules/leam.py:31-40, modules/layer_wise_norm.py:35-50,
  * modules/semantic_pe.py:36-48), fused; any subset via the use_* flags. fp32 in / fp32 out.
  * scratch for backward: fervit_premodules_scratch_floats(B, L, D) floats.

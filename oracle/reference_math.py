@@ -246,3 +246,79 @@ def grads_of(loss: Tensor, sd: Mapping[str, Tensor]) -> Dict[str, Tensor]:
     keys = [k for k, v in sd.items() if v.requires_grad]
     gs = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
     return {k: (g if g is not None else torch.zeros_like(sd[k])) for k, g in zip(keys, gs)}
+
+
+# ------------------------------------------------------------------------------------------------
+# Data-side prologue of the LatentViT train step: LatentAugment and mixup
+# ------------------------------------------------------------------------------------------------
+def latent_augment(latent: Tensor, noise_std: float, scale_range, mask_prob: float, normal: Optional[Tensor] = None,
+                   scale: Optional[Tensor] = None, keep: Optional[Tensor] = None) -> Tensor:
+    """``LatentAugment.__call__`` (data/latent_dataset.py:28-49) with the random draws injected: additive noise
+    ``normal * noise_std``, then one ``scale`` factor per sample, then the element mask ``keep``; a disabled stage
+    (``noise_std == 0`` / ``scale_range is None`` / ``mask_prob == 0``) is skipped as in the reference. ``latent`` is
+    one sample ``[18, 512]`` or a batch ``[B, 18, 512]`` (then ``scale`` is ``[B]``: the dataset augments per sample)."""
+    out = latent.clone()
+    if noise_std > 0:
+        out = out + normal.to(out.dtype) * noise_std
+    if scale_range is not None:
+        s = scale.to(out.dtype)
+        out = out * (s.reshape(-1, *([1] * (out.dim() - 1))) if out.dim() == 3 else s)
+    if mask_prob > 0:
+        out = out * keep.to(out.dtype)
+    return out
+
+
+def mixup(latents: Tensor, index: Tensor, lam: float) -> Tensor:
+    """``mixed_latents = lam * latents + (1 - lam) * latents[index]`` (train_latent_vit.py:126-127)."""
+    return lam * latents + (1 - lam) * latents[index]
+
+
+def mixup_loss(logits: Tensor, labels: Tensor, index: Tensor, lam: float, weight: Optional[Tensor] = None,
+               label_smoothing: float = 0.0) -> Tensor:
+    """``lam * criterion(logits, labels) + (1 - lam) * criterion(logits, labels[index])`` (train_latent_vit.py:131)."""
+    return (lam * cross_entropy(logits, labels, weight, label_smoothing)
+            + (1 - lam) * cross_entropy(logits, labels[index], weight, label_smoothing))
+
+
+# Counter-based draws of the device-side augmentation (include/fervit_b200.h: fervit_latent_batch). This is the
+# definition of the product's generator restated in numpy so that tests can replay the very draws the kernel used; the
+# reference draws from torch's global CPU generator, which no device kernel can reproduce.
+_SITE_NOISE, _SITE_SCALE, _SITE_MASK = 0x4C410000, 0x4C410002, 0x4C410003
+
+
+def mix_hash64(seed: int, site: int, idx):
+    """64-bit mix of (seed, site, idx) - fer_vit_b200/csrc/common.cuh: mix_hash64 (splitmix64 finaliser)."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        idx = np.asarray(idx, dtype=np.uint64)
+        z = (np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + np.uint64(0x9E3779B97F4A7C15) * np.uint64(site + 1)
+             + idx * np.uint64(0xD1B54A32D192ED03))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+
+
+def mix_hash(seed: int, site: int, idx):
+    """Its high word: the dropout generator of the kernels (common.cuh: mix_hash)."""
+    import numpy as np
+    return (mix_hash64(seed, site, idx) >> np.uint64(32)).astype(np.uint32)
+
+
+def latent_augment_draws(seed: int, B: int, row: int, scale_range=None, mask_prob: float = 0.0):
+    """(normal [B, row] f64, scale [B] f64, keep [B, row] bool) for batch positions 0..B-1 under `seed`, as
+    include/fervit_b200.h (fervit_latent_batch) defines them."""
+    import numpy as np
+    u = lambda h: ((h & np.uint64(0xFFFFFFFF)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 4294967296.0)
+    g = np.arange(B * row, dtype=np.uint64)
+    z = mix_hash64(seed, _SITE_NOISE, g >> np.uint64(1))
+    r = np.sqrt(-2.0 * np.log(u(z >> np.uint64(32)).astype(np.float64)))
+    t = 2.0 * np.pi * (u(z).astype(np.float64) - 0.5)
+    normal = np.where((g & np.uint64(1)) == 0, r * np.cos(t), r * np.sin(t)).reshape(B, row)
+    lo, hi = scale_range if scale_range is not None else (1.0, 1.0)
+    # the kernel forms the uniforms and the scale factor in fp32
+    uf = u(mix_hash64(seed, _SITE_SCALE, np.arange(B, dtype=np.uint64)) >> np.uint64(32))
+    scale = (np.float32(lo) + (np.float32(hi) - np.float32(lo)) * uf).astype(np.float64)
+    thr = max(1, int(float(np.float32(mask_prob)) * 65536.0)) if mask_prob > 0 else 0
+    lanes = (mix_hash64(seed, _SITE_MASK, g >> np.uint64(2)) >> (np.uint64(16) * (g & np.uint64(3)))) & np.uint64(0xFFFF)
+    keep = (lanes >= np.uint64(thr)).reshape(B, row)
+    return torch.from_numpy(normal), torch.from_numpy(scale), torch.from_numpy(keep)

@@ -1,0 +1,116 @@
+"""CPU: the data-side prologue of the LatentViT train step - the oracle's restatements against the
+golden vectors the UNMODIFIED reference produced (tests/golden/make_golden_data_path.py), the definition of the
+counter-based draws, and the host layer's error behaviour (no CPU path)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_math as R
+from tests.util import GOLDEN, load_golden, relerr
+
+CASES = ["all", "noise", "scale_mask", "off"]
+
+
+def load_augment(case):
+    z = np.load(os.path.join(GOLDEN, "latent_augment.npz"))
+    g = {k.split("/", 1)[1]: z[k] for k in z.files if k.startswith(case + "/")}
+    rng = tuple(float(v) for v in g["scale_range"]) if int(g["use_scale"]) else None
+    return g, float(g["noise_std"]), rng, float(g["mask_prob"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_latent_augment_matches_reference_golden(case):
+    g, std, rng, p = load_augment(case)
+    x = torch.from_numpy(g["x"])
+    out = R.latent_augment(x, std, rng, p, torch.from_numpy(g["normal"]), torch.tensor(float(g["scale"])),
+                           torch.from_numpy(g["keep"]))
+    assert torch.equal(out, torch.from_numpy(g["out"]))          # fp32: bit-exact with the reference
+    if case == "off":
+        assert torch.equal(out, x)
+    # batched form (one scale factor per sample) reduces to the per-sample form
+    xb = torch.stack([x, 2 * x])
+    nb = torch.stack([torch.from_numpy(g["normal"])] * 2)
+    kb = torch.stack([torch.from_numpy(g["keep"])] * 2)
+    ob = R.latent_augment(xb, std, rng, p, nb, torch.tensor([float(g["scale"]), 1.0]), kb)
+    assert torch.equal(ob[0], out)
+
+
+def test_oracle_mixup_step_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, "mixup_step.npz"))
+    g = load_golden("latent_vit")
+    x, y, index = torch.from_numpy(z["x"]), torch.from_numpy(z["y"]), torch.from_numpy(z["index"])
+    lam, w, eps = float(z["lam"]), torch.from_numpy(z["class_weight"]), float(z["label_smoothing"])
+    for dtype, tol_loss, tol_g in ((torch.float64, 1e-9, 1e-5), (torch.float32, 1e-5, 2e-4)):
+        sd = {k: (v.to(dtype).requires_grad_(True) if v.is_floating_point() else v) for k, v in g["sd"].items()}
+        logits = R.latent_vit_forward(sd, R.mixup(x.to(dtype), index, lam), 2, 2)
+        loss = R.mixup_loss(logits, y, index, lam, w.to(dtype), eps)
+        grads = R.grads_of(loss, sd)
+        assert abs(loss.item() - float(z["loss"])) < tol_loss
+        for k in grads:                                           # golden grads are stored in fp32
+            assert relerr(grads[k], torch.from_numpy(z["grad/" + k])) < tol_g, k
+        with torch.no_grad():                                     # the trainer's extra forward on the un-mixed batch
+            pred = R.latent_vit_forward(sd, x.to(dtype), 2, 2).argmax(-1)
+        assert torch.equal(pred, torch.from_numpy(z["pred"]))
+        assert abs((pred == y).double().mean().item() - float(z["accuracy"])) < 1e-12
+
+
+def test_mixup_loss_limits():
+    torch.manual_seed(1)
+    zl = torch.randn(9, 7, dtype=torch.float64)
+    y = torch.randint(0, 7, (9,))
+    idx = torch.randperm(9)
+    w = torch.rand(7, dtype=torch.float64) + 0.5
+    assert torch.allclose(R.mixup_loss(zl, y, idx, 1.0, w, 0.1), R.cross_entropy(zl, y, w, 0.1))
+    assert torch.allclose(R.mixup_loss(zl, y, idx, 0.0, w, 0.1), R.cross_entropy(zl, y[idx], w, 0.1))
+    assert torch.equal(R.mixup(zl, idx, 1.0), zl)
+
+
+def test_counter_based_draws_definition():
+    """Deterministic, position-keyed, and distributed as LatentAugment's draws (N(0,1), U(lo,hi), Bernoulli(1-p))."""
+    n, s, k = R.latent_augment_draws(42, 32, 9216, (0.9, 1.1), 0.1)
+    n2, s2, k2 = R.latent_augment_draws(42, 32, 9216, (0.9, 1.1), 0.1)
+    assert torch.equal(n, n2) and torch.equal(s, s2) and torch.equal(k, k2)
+    n3, _, k3 = R.latent_augment_draws(43, 32, 9216, (0.9, 1.1), 0.1)
+    assert not torch.equal(n, n3) and not torch.equal(k, k3)
+    # a prefix of the batch has the same draws: they depend on the batch position only
+    n4, s4, k4 = R.latent_augment_draws(42, 5, 9216, (0.9, 1.1), 0.1)
+    assert torch.equal(n4, n[:5]) and torch.equal(s4, s[:5]) and torch.equal(k4, k[:5])
+    assert abs(n.mean().item()) < 5e-3 and abs(n.std().item() - 1) < 5e-3
+    assert abs((n ** 4).mean().item() - 3) < 0.05                # Gaussian kurtosis
+    assert abs((n[:, 0::2] * n[:, 1::2]).mean().item()) < 5e-3   # the two normals of a Box-Muller pair are uncorrelated
+    assert 0.9 <= s.min().item() and s.max().item() <= 1.1 and s.std().item() > 0.03
+    assert abs(k.double().mean().item() - 0.9) < 2e-3
+    assert abs((k[:, :-1] & k[:, 1:]).double().mean().item() - 0.81) < 3e-3
+    # the 32-bit mix is the kernels' generator: known answers, so a change on either side is caught on the CPU
+    assert [int(v) for v in R.mix_hash(0, 0, np.arange(3))] == [int(v) for v in R.mix_hash(0, 0, [0, 1, 2])]
+    assert int(R.mix_hash(1234, 0x4C410003, 77)) == int(R.mix_hash(1234, 0x4C410003, [77])[0])
+
+
+def test_data_path_has_no_cpu_fallback(tmp_path):
+    import fer_vit_b200 as fv
+    x = torch.randn(4, 18, 512)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fv.latent_batch(x)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fv.LatentAugment(noise_std=0.1)(x[0])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fv.mixup(x, torch.randperm(4), 0.3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fv.mixup_cross_entropy(torch.randn(4, 7, requires_grad=True), torch.zeros(4, dtype=torch.long),
+                               torch.randperm(4), 0.3)
+    # directory errors of the reference dataset (data/latent_dataset.py:75-86)
+    with pytest.raises(FileNotFoundError):
+        fv.PackedLatentCache.from_dir(str(tmp_path / "missing"))
+    with pytest.raises(ValueError, match="No .pt files"):
+        fv.PackedLatentCache.from_dir(str(tmp_path))
+    torch.save({"latent": torch.randn(18, 512), "label": 3, "img_path": "a.png"}, tmp_path / "a.pt")
+    if not torch.cuda.is_available():
+        with pytest.raises((RuntimeError, AssertionError)):
+            fv.PackedLatentCache.from_dir(str(tmp_path))         # no GPU: refuses instead of keeping a host copy
+    # same constructor surface as the reference transform factories (data/latent_dataset.py:138-162)
+    t = fv.get_latent_train_transforms()
+    assert (t.noise_std, t.scale_range, t.mask_prob) == (0.1, (0.9, 1.1), 0.1)
+    assert fv.get_latent_val_transforms() is None
+    assert fv.LatentAugment().params() is None
