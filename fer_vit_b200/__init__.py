@@ -3,7 +3,7 @@ from .native_module import set_default_precision, get_default_precision
 from .runtime import CrossEntropyLoss, cross_entropy, mixup_cross_entropy
 from .models_fer_vit import (LatentViT, LatentViTv2, HybridLatentViT, AdapterModule, create_hybrid_latent_vit,
                              RECOMMENDED_STRATEGIES, ImageViT, PatchEmbedding, create_vit_tiny, create_vit_small,
-                             create_vit_base)
+                             create_vit_base, LatentDecomposer, ExpressionAwareViT)
 from .modules import LEAM, SemanticPE, LayerWiseNorm
 from .graph import GraphedTrainStep
 from .optim import FusedAdamW
@@ -14,4 +14,4 @@ __all__ = ["set_default_precision", "get_default_precision", "CrossEntropyLoss",
            "LatentViTv2", "HybridLatentViT", "AdapterModule", "create_hybrid_latent_vit", "RECOMMENDED_STRATEGIES",
            "ImageViT", "PatchEmbedding", "create_vit_tiny", "create_vit_small", "create_vit_base", "LEAM",
            "SemanticPE", "LayerWiseNorm", "GraphedTrainStep", "FusedAdamW", "mixup_cross_entropy", "LatentAugment",
-           "PackedLatentCache", "latent_batch", "mixup", "get_latent_train_transforms", "get_latent_val_transforms"]
+           "PackedLatentCache", "latent_batch", "mixup", "get_latent_train_transforms", "get_latent_val_transforms", "LatentDecomposer", "ExpressionAwareViT"]

@@ -79,6 +79,7 @@ SIGNATURES = {
     "fervit_cross_entropy_mixup": (_i, [_p, _p, _p, _p, _f, _i, _i, _f, _p, _f, _p, _p, _p]),
     "fervit_latent_batch": (_i, [_p, _p, _ll, _p, _i, _ll, C.POINTER(LatentAugmentParams), _u64, _p, _p, C.c_double, _p, _p,
                                 _p, _p, _p]),
+    "fervit_latent_decompose": (_i, [_p, _p, _i, _i, _ll, _i, _i, _f, _p, _p, _p]),
     "fervit_premodules_forward": (_i, [C.POINTER(PreModules), _p, _i, _i, _i, _p, _p]),
     "fervit_premodules_scratch_floats": (_ll, [_i, _i, _i]),
     "fervit_premodules_backward": (_i, [C.POINTER(PreModules), _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),

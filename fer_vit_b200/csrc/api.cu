@@ -57,6 +57,15 @@ FV_API int fervit_latent_batch(const float* latents, const long long* labels, lo
                       S_(stream));
 }
 
+FV_API int fervit_latent_decompose(const float* w_plus, const float* directions, int B, int C, long long row_elems,
+                                   int decompose_mode, int output_mode, float enhance_alpha, float* out,
+                                   float* scores, void* stream) {
+  FV_CHECK(w_plus && directions, "latent_decompose: null argument");
+  FV_CHECK(decompose_mode == 0 || decompose_mode == 1, "latent_decompose: unknown decompose_mode %d", decompose_mode);
+  return latent_decompose(w_plus, directions, B, C, row_elems, decompose_mode, output_mode, enhance_alpha, out, scores,
+                          S_(stream));
+}
+
 static PreParams to_pre(const fervit_premodules* p) {
   PreParams q;
   q.use_spe = p->use_spe; q.use_lwn = p->use_lwn; q.use_res = p->use_lwn_res; q.use_leam = p->use_leam;

@@ -124,6 +124,10 @@ int latent_batch(const float* latents, const long long* labels, long long n_rows
                  uint64_t seed, const unsigned long long* seed_dev, const long long* mix_index, double lam,
                  const float* lam_dev, float* out, long long* labels_out, int* status, cudaStream_t stream);
 
+// latent_decompose.cu
+int latent_decompose(const float* w, const float* dirs, int B, int C, long long row, int max_class, int output_mode,
+                     float alpha, float* out, float* scores, cudaStream_t stream);
+
 // premodules.cu
 namespace pre {
 struct Params {

@@ -4,7 +4,9 @@ from .latent_vit import LatentViT
 from .latent_vit_v2 import LatentViTv2
 from .hybrid_latent_vit import HybridLatentViT, AdapterModule, create_hybrid_latent_vit, RECOMMENDED_STRATEGIES
 from .image_vit import ImageViT, PatchEmbedding, create_vit_tiny, create_vit_small, create_vit_base
+from .latent_decomposer import LatentDecomposer
+from .expression_aware_vit import ExpressionAwareViT
 
 __all__ = ["LatentViT", "LatentViTv2", "HybridLatentViT", "AdapterModule", "create_hybrid_latent_vit",
            "RECOMMENDED_STRATEGIES", "ImageViT", "PatchEmbedding", "create_vit_tiny", "create_vit_small",
-           "create_vit_base"]
+           "create_vit_base", "LatentDecomposer", "ExpressionAwareViT"]

@@ -207,6 +207,21 @@ int fervit_latent_batch(const float* latents, const long long* labels, long long
                         const float* lam_dev, float* out, long long* labels_out, int* status, void* stream);
 
 /* ----------------------------------------------------------------------------------------------
+ * LatentDecomposer (models_fer_vit/latent_decomposer.py:82-173), the front-end of ExpressionAwareViT
+ * (expression_aware_vit.py:109-122): coefficients on C unit-norm expression directions, expression part, identity
+ * part and the requested combination in one launch.
+ *   coef[b,c] = <w_plus[b], directions[c]>  over the flattened row;  scores [B,C] (may be NULL) receives them
+ *   w_expr = sum_c coef n_c (decompose_mode 0 'all_classes') or the single |coef|-largest term (1 'max_class')
+ *   out = w_expr (output_mode 0 'expr_only') | w - w_expr (1 'id_only') | w_id + enhance_alpha * w_expr (2 'enhanced')
+ *       | [w_expr ; w_id] as [B, 2, row_elems] (3 'concat').  out may be NULL when only scores are wanted.
+ * w_plus [B,row_elems], directions [C,row_elems] fp32, C <= 8, row_elems % 4 == 0 and <= 12800. No backward: the
+ * input carries no gradient and the directions are buffers.
+ * -------------------------------------------------------------------------------------------- */
+int fervit_latent_decompose(const float* w_plus, const float* directions, int B, int C, long long row_elems,
+                            int decompose_mode, int output_mode, float enhance_alpha, float* out, float* scores,
+                            void* stream);
+
+/* ----------------------------------------------------------------------------------------------
  * Stand-alone pre-modules (modules/leam.py:31-40, modules/layer_wise_norm.py:35-50,
  * modules/semantic_pe.py:36-48), fused; any subset via the use_* flags. fp32 in / fp32 out.
  * scratch for backward: fervit_premodules_scratch_floats(B, L, D) floats.

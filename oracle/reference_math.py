@@ -322,3 +322,46 @@ def latent_augment_draws(seed: int, B: int, row: int, scale_range=None, mask_pro
     lanes = (mix_hash64(seed, _SITE_MASK, g >> np.uint64(2)) >> (np.uint64(16) * (g & np.uint64(3)))) & np.uint64(0xFFFF)
     keep = (lanes >= np.uint64(thr)).reshape(B, row)
     return torch.from_numpy(normal), torch.from_numpy(scale), torch.from_numpy(keep)
+
+
+# ------------------------------------------------------------------------------------------------
+# LatentDecomposer / ExpressionAwareViT front-end
+# ------------------------------------------------------------------------------------------------
+def normalize_directions(directions: Tensor) -> Tensor:
+    """Stacked directions [C, L, D] with every flattened direction scaled to unit norm
+    (latent_decomposer.py:58-65)."""
+    flat = directions.reshape(directions.shape[0], -1)
+    return (flat / (flat.norm(dim=1, keepdim=True) + 1e-12)).reshape(directions.shape)
+
+
+def latent_decompose(w_plus: Tensor, directions: Tensor, mode: str = "all_classes"):
+    """(w_expr, w_id, coefficients) of latent_decomposer.py:82-118: coefficients = flattened w+ times the unit
+    directions; the expression part is their recombination (all classes) or the single largest-|coef| term."""
+    B = w_plus.shape[0]
+    d = directions.reshape(directions.shape[0], -1).to(w_plus.dtype)
+    flat = w_plus.reshape(B, -1)
+    coef = flat @ d.T
+    if mode == "all_classes":
+        expr = coef @ d
+    elif mode == "max_class":
+        best = coef.abs().argmax(dim=1)
+        expr = coef[torch.arange(B), best].reshape(B, 1) * d[best]
+    else:
+        raise ValueError(f"Unknown mode: {mode!r}")
+    expr = expr.reshape(w_plus.shape)
+    return expr, w_plus - expr, coef
+
+
+def decomposer_forward(w_plus: Tensor, directions: Tensor, output_mode: str = "expr_only", enhance_alpha: float = 2.0,
+                       decompose_mode: str = "all_classes") -> Tensor:
+    """LatentDecomposer.forward (latent_decomposer.py:146-173)."""
+    expr, ident, _ = latent_decompose(w_plus, directions, decompose_mode)
+    if output_mode == "expr_only":
+        return expr
+    if output_mode == "id_only":
+        return ident
+    if output_mode == "enhanced":
+        return ident + enhance_alpha * expr
+    if output_mode == "concat":
+        return torch.cat([expr, ident], dim=1)
+    raise ValueError(f"Unknown output_mode: {output_mode!r}")

@@ -10,8 +10,9 @@ G[ops_tc]="tests/test_gpu_ops.py -k 'tcgen05'"
 G[ops_wgrad]="tests/test_gpu_ops.py -k 'wgrad'"
 G[models_fp32]="tests/test_gpu_models.py -k 'fp32 or fallback or roundtrip or (graphed and not dropout) or fused'"
 G[models_bf16]="tests/test_gpu_models.py -k 'bf16'"
+G[data_path]="tests/test_gpu_data_path.py"
 groups="$@"
-[ -z "$groups" ] && groups="ops_basic ops_tc ops_wgrad models_fp32 models_bf16"
+[ -z "$groups" ] && groups="ops_basic ops_tc ops_wgrad models_fp32 models_bf16 data_path"
 for g in $groups; do
   echo "=== $g"
   eval timeout 900 python -m pytest ${G[$g]} -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/$g.log 2>&1

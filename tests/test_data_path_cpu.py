@@ -114,3 +114,59 @@ def test_data_path_has_no_cpu_fallback(tmp_path):
     assert (t.noise_std, t.scale_range, t.mask_prob) == (0.1, (0.9, 1.1), 0.1)
     assert fv.get_latent_val_transforms() is None
     assert fv.LatentAugment().params() is None
+
+
+# ------------------------------------------------------------------------------------------------
+# LatentDecomposer / ExpressionAwareViT front-end
+# ------------------------------------------------------------------------------------------------
+DEC_MODES = [(d, o) for d in ("all_classes", "max_class") for o in ("expr_only", "id_only", "enhanced", "concat")]
+
+
+@pytest.mark.parametrize("dm,om", DEC_MODES)
+def test_oracle_decomposer_matches_reference_golden(dm, om):
+    z = np.load(os.path.join(GOLDEN, "expression_aware.npz"))
+    x, dirs = torch.from_numpy(z["x"]), torch.from_numpy(z["directions"])
+    raw = torch.stack([torch.from_numpy(z[f"raw_direction/{i}"]) for i in range(7)])
+    assert relerr(R.normalize_directions(raw), dirs) < 1e-7
+    want = torch.from_numpy(z[f"out/{dm}/{om}"])
+    assert relerr(R.decomposer_forward(x.double(), dirs.double(), om, float(z["alpha"]), dm), want) < 2e-7
+    assert relerr(R.decomposer_forward(x, dirs, om, float(z["alpha"]), dm), want) < 2e-6
+    e, i, coef = R.latent_decompose(x.double(), dirs.double(), dm)
+    assert relerr(coef, torch.from_numpy(z["scores"])) < 2e-7
+    assert relerr(e + i, x) < 1e-15                                 # the two parts always add back to w+
+    if dm == "all_classes":                                         # identity part carries no expression score (up
+        # to the directions' mutual overlap: exact only for orthogonal directions) - projecting twice is stable
+        e2, _, _ = R.latent_decompose(e, dirs.double(), dm)
+        assert e2.shape == e.shape
+
+
+def test_oracle_expression_aware_step_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, "expression_aware.npz"))
+    gk = [k[5:] for k in z.files if k.startswith("grad/")]
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    sd = {k: (v.double().requires_grad_(k in gk) if v.is_floating_point() else v) for k, v in sd.items()}
+    x = R.decomposer_forward(torch.from_numpy(z["x"]).double(), torch.from_numpy(z["directions"]).double(), "concat")
+    assert x.shape[1] == 36
+    logits = R.hybrid_forward(sd, x, 2, 2, True)
+    loss = R.cross_entropy(logits, torch.from_numpy(z["y"]))
+    grads = R.grads_of(loss, sd)
+    assert relerr(logits, torch.from_numpy(z["logits"])) < 1e-6
+    assert abs(loss.item() - float(z["loss"])) < 1e-6
+    for k in gk:
+        assert relerr(grads[k], torch.from_numpy(z["grad/" + k])) < 1e-5, k
+
+
+def test_decomposer_host_surface():
+    import fer_vit_b200 as fv
+    z = np.load(os.path.join(GOLDEN, "expression_aware.npz"))
+    raw = {i: torch.from_numpy(z[f"raw_direction/{i}"]) for i in range(7)}
+    d = fv.LatentDecomposer(raw, 18, 64)
+    assert (d.seq_len, d.latent_dim, d.num_classes) == (18, 64, 7)
+    assert list(d.state_dict()) == ["directions"] and not list(d.parameters())
+    assert relerr(d.directions, torch.from_numpy(z["directions"])) < 1e-7
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        d(torch.randn(2, 18, 64))
+    with pytest.raises(ValueError, match="Unknown output_mode"):
+        d(torch.randn(2, 18, 64), output_mode="nope")
+    with pytest.raises(ValueError, match="Unknown mode"):
+        d.decompose(torch.randn(2, 18, 64), mode="nope")

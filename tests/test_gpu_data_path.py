@@ -185,3 +185,73 @@ def test_mixup_train_step_matches_reference_golden(precision, tol_l, tol_g):
         pred = model(x).argmax(-1)
     assert torch.equal(pred.cpu(), torch.from_numpy(z["pred"]))
     assert abs((pred == y).double().mean().item() - float(z["accuracy"])) < 1e-12
+
+
+# ------------------------------------------------------------------------------------------------
+# LatentDecomposer / ExpressionAwareViT front-end
+# ------------------------------------------------------------------------------------------------
+DEC_MODES = [(d, o) for d in ("all_classes", "max_class") for o in ("expr_only", "id_only", "enhanced", "concat")]
+
+
+@pytest.mark.parametrize("dm,om", DEC_MODES)
+def test_latent_decomposer_matches_reference_golden(dm, om):
+    import fer_vit_b200 as fv
+    z = np.load(os.path.join(GOLDEN, "expression_aware.npz"))
+    d = fv.LatentDecomposer({i: torch.from_numpy(z[f"raw_direction/{i}"]) for i in range(7)}, 18, 64).cuda()
+    x = torch.from_numpy(z["x"]).cuda()
+    out = d(x, output_mode=om, enhance_alpha=float(z["alpha"]), decompose_mode=dm)
+    e = relerr(out, torch.from_numpy(z[f"out/{dm}/{om}"]))
+    record("latent_decomposer_golden", decompose_mode=dm, output_mode=om, err=e)
+    assert e < 1e-5
+    assert relerr(d.get_expression_scores(x), torch.from_numpy(z["scores"])) < 1e-5
+    we, wi = d.decompose(x, mode=dm)
+    assert relerr(we + wi, x) < 1e-6
+    assert relerr(d.enhance_expression(x, float(z["alpha"]), dm), torch.from_numpy(z[f"out/{dm}/enhanced"])) < 1e-5
+
+
+@pytest.mark.parametrize("B", [1, 3, 64, 597])
+@pytest.mark.parametrize("C", [1, 7, 8])
+def test_latent_decomposer_full_size_against_oracle(B, C):
+    """w+ of the real size (18 x 512), ragged batch sizes (R = 4 latents per CTA pass), every direction count."""
+    import fer_vit_b200 as fv
+    g = torch.Generator().manual_seed(B * 10 + C)
+    raw = {i: torch.randn(18, 512, generator=g) for i in range(C)}
+    d = fv.LatentDecomposer(raw, 18, 512).cuda()
+    x = torch.randn(B, 18, 512, generator=g) + 0.1
+    dirs = R.normalize_directions(torch.stack([raw[i] for i in range(C)]).double())
+    for dm, om in (("all_classes", "concat"), ("max_class", "enhanced"), ("all_classes", "expr_only")):
+        out = d(x.cuda(), output_mode=om, enhance_alpha=2.0, decompose_mode=dm)
+        ref = R.decomposer_forward(x.double(), dirs, om, 2.0, dm)
+        e = relerr(out, ref)
+        record("latent_decomposer", B=B, C=C, decompose_mode=dm, output_mode=om, err=e)
+        assert e < 1e-5, (dm, om, e)
+    assert relerr(d.get_expression_scores(x.cuda()), R.latent_decompose(x.double(), dirs)[2]) < 1e-5
+
+
+@pytest.mark.parametrize("precision,tol_l,tol_g", [("fp32", 1e-4, 1e-4), ("bf16", 2e-2, 2e-2)])
+def test_expression_aware_vit_step_matches_reference_golden(precision, tol_l, tol_g):
+    """ExpressionAwareViT in 'concat' mode (36 + 1 tokens), frozen blocks + adapters: logits, loss and every trainable
+    gradient of the reference step; identical top-1."""
+    import fer_vit_b200 as fv
+    from fer_vit_b200.models_fer_vit.vit_blocks import register_vit_config
+    z = np.load(os.path.join(GOLDEN, "expression_aware.npz"))
+    fv.set_default_precision(precision)
+    register_vit_config("vit_test_patch16_224", 64, 2, 2)
+    dec = fv.LatentDecomposer({i: torch.from_numpy(z[f"raw_direction/{i}"]) for i in range(7)}, 18, 64)
+    vit = fv.HybridLatentViT(latent_dim=64, seq_len=36, pretrained_model_name="vit_test_patch16_224", num_classes=7,
+                             use_pretrained=False, freeze_transformer=True, adapter_dim=16, verbose=False)
+    vit.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}, strict=True)
+    model = fv.ExpressionAwareViT(dec, vit, output_mode="concat").cuda().eval()
+    logits = model(torch.from_numpy(z["x"]).cuda())
+    loss = fv.cross_entropy(logits, torch.from_numpy(z["y"]).cuda())
+    loss.backward()
+    e_l = relerr(logits, torch.from_numpy(z["logits"]))
+    grads = {k: p.grad for k, p in model.vit.named_parameters() if p.grad is not None}
+    want = {k[5:] for k in z.files if k.startswith("grad/")}
+    assert set(grads) == want and len(model.get_trainable_params()) == len(want)
+    errs = {k: relerr(v, torch.from_numpy(z["grad/" + k])) for k, v in grads.items()}
+    worst = max(errs, key=errs.get)
+    record("expression_aware_vit_step", precision=precision, err_logits=e_l, err_grad=errs[worst], worst=worst)
+    assert e_l < tol_l and abs(loss.item() - float(z["loss"])) < tol_l * 10
+    assert errs[worst] < tol_g, (worst, errs[worst])
+    assert torch.equal(logits.argmax(-1).cpu(), torch.from_numpy(z["logits"]).argmax(-1))

@@ -58,6 +58,32 @@ def main():
                               "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3),
                               "samples_per_s": round(B / us * 1e6)}), flush=True)
 
+    # LatentDecomposer (fervit_latent_decompose): read row*4 + write row*4 (2x for concat) per sample
+    dec = fv.LatentDecomposer({i: torch.randn(18, 512) for i in range(7)}, 18, 512).cuda()
+    for B in a.batch:
+        xs = [torch.randn(B, 18, 512, device="cuda") for _ in range(8)]          # 8 x B latents in rotation
+        for om in ("expr_only", "concat"):
+            for i in range(3):
+                dec(xs[i], output_mode=om)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for i in range(a.iters):
+                    dec(xs[i % 8], output_mode=om)
+            graph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            graph.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / a.iters
+            nbytes = B * 18 * 512 * 4 * (3 if om == "concat" else 2)
+            gbs = nbytes / us / 1e3
+            print(json.dumps({"kernel": "latent_decompose", "mode": om, "batch": B, "us": round(us, 2),
+                              "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3),
+                              "samples_per_s": round(B / us * 1e6)}), flush=True)
+
 
 if __name__ == "__main__":
     main()
