@@ -5,7 +5,7 @@ from .models_fer_vit import (LatentViT, LatentViTv2, HybridLatentViT, AdapterMod
                              RECOMMENDED_STRATEGIES, ImageViT, PatchEmbedding, create_vit_tiny, create_vit_small,
                              create_vit_base, LatentDecomposer, ExpressionAwareViT)
 from .modules import LEAM, SemanticPE, LayerWiseNorm
-from .graph import GraphedTrainStep
+from .graph import GraphedTrainStep, GraphedMixupTrainStep
 from .optim import FusedAdamW
 from .data import (LatentAugment, PackedLatentCache, latent_batch, mixup, get_latent_train_transforms,
                    get_latent_val_transforms)
@@ -13,5 +13,5 @@ from .data import (LatentAugment, PackedLatentCache, latent_batch, mixup, get_la
 __all__ = ["set_default_precision", "get_default_precision", "CrossEntropyLoss", "cross_entropy", "LatentViT",
            "LatentViTv2", "HybridLatentViT", "AdapterModule", "create_hybrid_latent_vit", "RECOMMENDED_STRATEGIES",
            "ImageViT", "PatchEmbedding", "create_vit_tiny", "create_vit_small", "create_vit_base", "LEAM",
-           "SemanticPE", "LayerWiseNorm", "GraphedTrainStep", "FusedAdamW", "mixup_cross_entropy", "LatentAugment",
+           "SemanticPE", "LayerWiseNorm", "GraphedTrainStep", "GraphedMixupTrainStep", "FusedAdamW", "mixup_cross_entropy", "LatentAugment",
            "PackedLatentCache", "latent_batch", "mixup", "get_latent_train_transforms", "get_latent_val_transforms", "LatentDecomposer", "ExpressionAwareViT"]

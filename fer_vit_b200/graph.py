@@ -34,14 +34,18 @@ class GraphedTrainStep:
         self.loss_fn = loss_fn or runtime.cross_entropy
         self.static_x = example_x.detach().clone()
         self.static_y = example_y.detach().clone()
+        self._capture(example_x.device, warmup)
+
+    def _capture(self, device, warmup: int) -> None:
+        model, optimizer = self.model, self.optimizer
         runner = model.plan_runner()
         if runner.seed_dev is None:
             # dropout masks are a pure function of (seed, site, element); the captured host seed is fixed, this device
             # counter (incremented inside the graph) makes every replay draw fresh masks
-            runner.seed_dev = torch.zeros(1, dtype=torch.int64, device=example_x.device)
+            runner.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
         self._seed_dev = runner.seed_dev
 
-        side = torch.cuda.Stream(device=example_x.device)
+        side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(max(1, warmup)):      # allocator, cuBLAS-free: warms the caching allocator and NCCL
@@ -77,3 +81,61 @@ class GraphedTrainStep:
         self.graph.replay()
         self.replays += 1
         return self.static_loss
+
+
+class GraphedMixupTrainStep(GraphedTrainStep):
+    """The LatentViT trainers' whole step (train_latent_vit.py:115-142) as one graph replay, fed from a
+    ``PackedLatentCache``: gather + ``LatentAugment`` + mixup -> zero_grad -> forward -> mixup loss -> backward ->
+    optimizer step -> (optionally) the trainer's no-grad forward on the un-mixed batch for train accuracy.
+
+        step = GraphedMixupTrainStep(model, optimizer, cache, batch_size, criterion)     # fer_vit_b200.CrossEntropyLoss
+        loss, correct = step(sample_idx, mix_index, lam)     # device index tensors [batch_size], python float lam
+
+    ``loss`` and ``correct`` (number of correct predictions of the accuracy pass, or None) are static device tensors;
+    read them off the hot path. The augmentation draws a fresh stream per replay (device-side seed counter); the
+    accuracy pass sees the same augmented latents as the training pass, as in the reference (augmentation happens in
+    the dataset, before mixup)."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, cache, batch_size: int,
+                 criterion=None, train_accuracy: bool = True, seed: int = 0, warmup: int = 3):
+        dev = cache.latents.device
+        for grp in optimizer.param_groups:
+            if not grp.get("capturable", False):
+                raise RuntimeError("fer_vit_b200: GraphedMixupTrainStep needs an optimizer built with capturable=True")
+        self.model = model
+        self.optimizer = optimizer
+        self.cache = cache
+        self.criterion = criterion or runtime.CrossEntropyLoss()
+        self.train_accuracy = train_accuracy
+        self.seed = int(seed)
+        self.static_idx = torch.arange(batch_size, device=dev) % len(cache)
+        self.static_mix = torch.arange(batch_size, device=dev)
+        self.static_lam = torch.ones(1, dtype=torch.float32, device=dev)
+        self.static_correct = None
+        self._capture(dev, warmup)
+
+    def _eager(self) -> torch.Tensor:
+        self._seed_dev.add_(1)
+        c = self.cache
+        mixed, labels = c.batch(self.static_idx, self.static_mix, self.static_lam, self.seed, self._seed_dev)
+        self.optimizer.zero_grad(set_to_none=True)
+        logits = self.model(mixed)
+        loss = self.criterion.mixup(logits, labels, self.static_mix, self.static_lam)
+        loss.backward()
+        self.optimizer.step()
+        if self.train_accuracy:
+            with torch.no_grad():
+                clean, _ = c.batch(self.static_idx, None, 1.0, self.seed, self._seed_dev)
+                self.static_correct = (self.model(clean).argmax(dim=1) == labels).sum()
+        return loss.detach()
+
+    def __call__(self, sample_idx: torch.Tensor, mix_index: torch.Tensor, lam: float):
+        if sample_idx.shape != self.static_idx.shape or mix_index.shape != self.static_mix.shape:
+            raise RuntimeError(f"fer_vit_b200: GraphedMixupTrainStep was captured for batches of "
+                               f"{self.static_idx.numel()}, got {sample_idx.numel()} / {mix_index.numel()}")
+        self.static_idx.copy_(sample_idx, non_blocking=True)
+        self.static_mix.copy_(mix_index, non_blocking=True)
+        self.static_lam.fill_(float(lam))
+        self.graph.replay()
+        self.replays += 1
+        return self.static_loss, self.static_correct

@@ -255,3 +255,51 @@ def test_expression_aware_vit_step_matches_reference_golden(precision, tol_l, to
     assert e_l < tol_l and abs(loss.item() - float(z["loss"])) < tol_l * 10
     assert errs[worst] < tol_g, (worst, errs[worst])
     assert torch.equal(logits.argmax(-1).cpu(), torch.from_numpy(z["logits"]).argmax(-1))
+
+
+def test_graphed_mixup_train_step_matches_eager():
+    """GraphedMixupTrainStep = the LatentViT trainer's whole step (batch from the packed cache with augmentation and
+    mixup, mixup loss, backward, AdamW, accuracy pass) as one graph replay: bit-identical parameters, losses and
+    correct-counts with the same step composed eagerly from the public pieces, including the per-replay seed."""
+    import copy
+    import fer_vit_b200 as fv
+    g = load_golden("latent_vit")
+    m1 = build_model("latent_vit", "bf16")
+    m1.load_state_dict(g["sd"], strict=True)
+    m1 = m1.cuda().train()                      # dropout 0.0 in this fixture: no masks drawn
+    m2 = copy.deepcopy(m1)
+    gen = torch.Generator().manual_seed(12)
+    N, B = 40, 16
+    lat = torch.randn(N, 18, 64, generator=gen)
+    lab = torch.randint(0, 7, (N,), generator=gen)
+    aug = fv.LatentAugment(0.1, (0.9, 1.1), 0.1)
+    cache = fv.PackedLatentCache(lat, lab, aug)
+    crit = fv.CrossEntropyLoss(torch.tensor([1.0, 2.0, 0.5, 1.0, 1.5, 0.7, 1.2]).cuda(), 0.1)
+    o1 = fv.FusedAdamW(m1.parameters(), lr=1e-3)
+    o2 = fv.FusedAdamW(m2.parameters(), lr=1e-3)
+    stepper = fv.GraphedMixupTrainStep(m2, o2, cache, B, crit, seed=1000, warmup=3)
+    assert stepper.launches_per_replay > 30
+
+    def eager(idx, mix, lam, k):                # k = value of the device seed counter during that step
+        mixed, labels = cache.batch(idx, mix, lam, seed=1000 + k)
+        o1.zero_grad(set_to_none=True)
+        loss = crit.mixup(m1(mixed), labels, mix, lam)
+        loss.backward()
+        o1.step()
+        with torch.no_grad():
+            clean, _ = cache.batch(idx, None, 1.0, seed=1000 + k)
+            correct = (m1(clean).argmax(1) == labels).sum()
+        return float(loss.detach()), int(correct)
+
+    ar = torch.arange(B, device="cuda")
+    for k in (1, 2, 3):                         # the three warm-up steps of the constructor (identity batch, lam = 1)
+        eager(ar % N, ar, 1.0, k)
+    for s, lam in enumerate((0.348, 0.9, 0.05)):
+        idx = torch.randint(0, N, (B,), generator=gen).cuda()
+        mix = torch.randperm(B, generator=gen).cuda()
+        l1, c1 = eager(idx, mix, float(np.float32(lam)), 4 + s)
+        l2, c2 = stepper(idx, mix, lam)
+        assert (l1, c1) == (float(l2), int(c2)), (s, l1, float(l2), c1, int(c2))
+    for (k, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(a, b), k
+    cache.check()
