@@ -38,6 +38,34 @@ def run(name, model, x, y, steps, smoothing):
                       "loss": round(float(step(x, y)), 4)}), flush=True)
 
 
+def run_trainer_step(name, model, B, steps):
+    """The LatentViT trainers' whole step (train_latent_vit.py:115-142) from a packed latent cache: gather + the
+    default train augmentation + mixup, mixup loss (label smoothing 0.1), backward, AdamW, and the extra no-grad
+    forward for train accuracy - one graph replay per step."""
+    model = model.cuda().train()
+    N = 16384                                              # 16,384 latents = 604 MB (> L2)
+    cache = fv.PackedLatentCache(torch.randn(N, 18, 512), torch.randint(0, 7, (N,)), fv.get_latent_train_transforms())
+    opt = fv.FusedAdamW(model.parameters(), lr=1e-4, weight_decay=0.01)
+    step = fv.GraphedMixupTrainStep(model, opt, cache, B, fv.CrossEntropyLoss(None, 0.1))
+    idx = [torch.randint(0, N, (B,), device="cuda") for _ in range(8)]
+    mix = [torch.randperm(B, device="cuda") for _ in range(8)]
+    for i in range(3):
+        step(idx[i], mix[i], 0.4)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(steps):
+        step(idx[i % 8], mix[i % 8], 0.4)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    loss, correct = step(idx[0], mix[0], 0.4)
+    cache.check()
+    print(json.dumps({"config": name, "batch": B, "ms_per_step": round(ms, 3),
+                      "samples_per_s": round(B / ms * 1e3, 1), "launches_per_step": step.launches_per_replay,
+                      "loss": round(float(loss), 4), "train_correct": int(correct)}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
@@ -51,6 +79,10 @@ def main():
     run("1: LatentViT 512/6/8/2048", fv.LatentViT(), lat(32), lab(32), a.steps, 0.1)
     run("4: LatentViTv2 all pre-modules", fv.LatentViTv2(use_lwn=True, use_lwn_residual=True, use_spe=True,
                                                          use_leam=True), lat(512), lab(512), a.steps, 0.1)
+    run_trainer_step("4 + data path: LatentViTv2, cache batch + augment + mixup + accuracy pass",
+                     fv.LatentViTv2(use_lwn=True, use_lwn_residual=True, use_spe=True, use_leam=True), 512, a.steps)
+    run_trainer_step("1 + data path: LatentViT, cache batch + augment + mixup + accuracy pass", fv.LatentViT(), 32,
+                     a.steps)
     run("2: ImageViT 512/6/8/2048 @224", fv.ImageViT(embed_dim=512, depth=6, heads=8, mlp_dim=2048),
         torch.randn(64, 3, 224, 224, device="cuda", generator=g), lab(64), a.steps, 0.0)
 
