@@ -84,6 +84,8 @@ SIGNATURES = {
     "fervit_premodules_scratch_floats": (_ll, [_i, _i, _i]),
     "fervit_premodules_backward": (_i, [C.POINTER(PreModules), _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "fervit_linear_forward": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "fervit_gemm_scratch_bytes": (_ll, []),
+    "fervit_set_gemm_scratch": (_i, [_p, _ll]),
     "fervit_debug_gemm_clock": (_i, [_p, _p]),
     "fervit_adapter_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),
     "fervit_adapter_backward_input": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),

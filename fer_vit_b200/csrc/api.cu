@@ -139,6 +139,9 @@ FV_API int fervit_adamw_step(int n, void* const* params, void* const* grads, voi
                     hyper, step, max_norm, scratch, S_(stream));
 }
 
+FV_API long long fervit_gemm_scratch_bytes(void) { return (long long)gemm_tc2_scratch_bytes(); }
+FV_API int fervit_set_gemm_scratch(void* ptr, long long bytes) { return gemm_tc2_set_scratch(ptr, (size_t)bytes); }
+
 FV_API int fervit_debug_gemm_clock(double* ns, double* cycles) {
   FV_CHECK(ns && cycles, "debug_gemm_clock: null argument");
   return gemm_tc2_clock_probe(ns, cycles);

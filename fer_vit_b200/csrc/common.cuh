@@ -261,6 +261,8 @@ struct Epilogue {
   const float* pos;        // [(L+1), N] position rows, used with remap_L
   int ldo;                 // leading dimension of out / out_f32 / residual (elements)
   Dropout drop;
+  void* sk_ws;             // stream-K scratch of the CTA-pair GEMM (gemm_tc2.cu), zero-initialised flags first; or null
+  size_t sk_bytes;
 };
 
 static inline Epilogue make_epilogue() {

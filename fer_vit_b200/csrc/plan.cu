@@ -86,6 +86,7 @@ struct fervit_plan {
   std::vector<size_t> wb_off, wbt_off;  // byte offsets into the weight cache per slot (SIZE_MAX = not cached)
   size_t wcache_bytes;
   char* wcache;
+  size_t sk_off = SIZE_MAX, sk_bytes = 0;  // stream-K scratch of the CTA-pair GEMM, inside the weight cache buffer
   int bwd_cur;  // which of dx[0]/dx[1] holds the running gradient between backward stages
   // Side stream of the backward pass: the adapter weight-gradient GEMMs and column sums do not feed the dgrad chain,
   // so they run beside it and fill the SMs the chain leaves idle (57-tile GEMMs, partial last waves). Fork/join by
@@ -310,8 +311,18 @@ int linear(const Ctx& c, const AT* A, int M, int slot, bool transposed, const Ep
     if (!transposed) return gemm_f32_simt(A, Kin, 1, W, Kin, 1, M, Nout, Kin, 1, epi, c.st);
     return gemm_f32_simt(A, Nout, 1, W, 1, Kin, M, Kin, Nout, 1, epi, c.st);
   } else {
-    if (!transposed) return gemm_bf16_tc(A, Kin, false, c.p->WB(slot), Kin, false, M, Nout, Kin, 1, 0, epi, c.st);
-    return gemm_bf16_tc(A, Nout, false, c.p->WBT(slot), Nout, false, M, Kin, Nout, 1, 0, epi, c.st);
+    Epilogue e2 = epi;
+    static int sk_on = -1;   // opt-in: measured slower at batch 256 (gemm_tc2.cu: Params), and it gives up the
+    if (sk_on < 0) {         // batch-invariance of the results (the summation order then depends on the tile count)
+      const char* s = getenv("FERVIT_GEMM_STREAMK");
+      sk_on = (s && atoi(s) == 1) ? 1 : 0;
+    }
+    if (sk_on && c.p->sk_bytes && c.st != c.p->side) {   // main-stream GEMMs run one after another: one region serves all
+      e2.sk_ws = c.p->wcache + c.p->sk_off;
+      e2.sk_bytes = c.p->sk_bytes;
+    }
+    if (!transposed) return gemm_bf16_tc(A, Kin, false, c.p->WB(slot), Kin, false, M, Nout, Kin, 1, 0, e2, c.st);
+    return gemm_bf16_tc(A, Nout, false, c.p->WBT(slot), Nout, false, M, Kin, Nout, 1, 0, e2, c.st);
   }
 }
 
@@ -839,6 +850,12 @@ FV_API int fervit_plan_create(const fervit_config* cfg, fervit_plan** out) {
       }
     }
   }
+  if (c.mode == FERVIT_BF16) {
+    off = (off + 255) & ~size_t(255);
+    p->sk_off = off;
+    p->sk_bytes = gemm_tc2_scratch_bytes();
+    off += p->sk_bytes;
+  }
   p->wcache_bytes = off;
   *out = p;
   return 0;
@@ -870,6 +887,11 @@ FV_API int fervit_plan_set_wcache(fervit_plan* plan, void* ptr, long long bytes)
   FV_CHECK(bytes >= (long long)plan->wcache_bytes, "set_wcache: buffer too small");
   FV_CHECK(plan->wcache_bytes == 0 || ((uintptr_t)ptr & 255) == 0, "set_wcache: buffer must be 256-byte aligned");
   plan->wcache = reinterpret_cast<char*>(ptr);
+  if (plan->sk_bytes) {
+    // arrival flags of the stream-K GEMMs start at zero and every launch leaves them at zero (set-up path: blocking)
+    FV_CUDA(cudaMemset(plan->wcache + plan->sk_off, 0, 4096));
+    FV_CUDA(cudaDeviceSynchronize());
+  }
   return 0;
 }
 

@@ -317,6 +317,14 @@ int fervit_adamw_step(int n, void* const* params, void* const* grads, void* cons
                       const long long* numel, const int* group, const float* hyper, float* step, float max_norm,
                       float* scratch, void* stream);
 
+/* Stream-K scratch for the stand-alone GEMM entry points (fervit_linear_forward / fervit_linear_dgrad): when a GEMM's
+ * last round of 256 x 256 tiles under-fills the GPU (e.g. 57 tiles on 74 SM pairs) and K >= 1024, the tiles of that
+ * round are split along K across all pairs and the fp32 partial accumulators travel through this buffer. ptr: device
+ * buffer of fervit_gemm_scratch_bytes() bytes, 256-byte aligned, whose first 4096 bytes are zero, alive until replaced;
+ * NULL switches stream-K off for these entry points. Plans carry their own region inside the weight cache. */
+long long fervit_gemm_scratch_bytes(void);
+int fervit_set_gemm_scratch(void* ptr, long long bytes);
+
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 8 set, the CTA-pair GEMM records the wall time (ns, %globaltimer) and the SM
  * cycle count (clock64) of its CTA 0; cycles / ns = the SM clock in GHz while the kernel ran. */
 int fervit_debug_gemm_clock(double* ns, double* cycles);

@@ -175,6 +175,43 @@ def test_gemm_bf16_tcgen05_pair(lib, M, N, K, bn):
     record("gemm_bf16_tcgen05_pair", M=M, N=N, K=K, bn=bn, **errs)
 
 
+@pytest.mark.parametrize("M,N,K", [(4864, 768, 3072), (4864, 768, 2304), (4700, 768, 3072), (9728, 768, 3072),
+                                   (4864, 2304, 1024), (4864, 768, 1024), (19 * 64, 768, 3072)])
+def test_gemm_bf16_tcgen05_stream_k(lib, M, N, K):
+    """Stream-K over the under-filled last round of the CTA-pair GEMM (57 tiles on 74 pairs at batch 256; 74 + 40 at
+    batch 512; 148 + 23 for the QKV shape; a 15-tile problem spread over all pairs): bf16 output, fp32 residual output
+    (single-tile aliased staging) and dgrad, against fp64 math on the same inputs; deterministic and re-armed (two
+    launches bit-identical); within fp32 rounding of the same GEMM without stream-K."""
+    L = lib
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 7 * K)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g)
+    acc = x.double() @ W.double().t()
+    base_bf, base_f32, _ = run_linear(L, L.BF16, x, W, b, r, L.ACT_NONE, True, True, False, 0)     # scratch unset
+    nbytes = int(L.lib().fervit_gemm_scratch_bytes())
+    scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().fervit_set_gemm_scratch(scratch.data_ptr(), nbytes))
+    try:
+        out1, of1, _ = run_linear(L, L.BF16, x, W, b, r, L.ACT_NONE, True, True, False, 0)
+        out2, of2, _ = run_linear(L, L.BF16, x, W, b, r, L.ACT_NONE, True, True, False, 0)
+        ob, _, _ = run_linear(L, L.BF16, x, W, b, None, L.ACT_NONE, True, False, False, 0)
+        dg = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+        L.check(L.lib().fervit_linear_dgrad(L.BF16, x.data_ptr(), W.data_ptr(), None, None, M, K, N, L.ACT_NONE,
+                                            dg.data_ptr(), None, 0, st()))
+        torch.cuda.synchronize()
+        assert int(scratch[:4096].view(torch.int32).abs().sum()) == 0, "arrival flags must be back at zero"
+    finally:
+        L.check(L.lib().fervit_set_gemm_scratch(None, 0))
+    e = {"f32": relerr(of1, acc + b + r), "bf16": relerr(ob.float(), acc + b), "dgrad": relerr(dg.float(), acc),
+         "vs_plain": relerr(of1, base_f32)}
+    record("gemm_bf16_tcgen05_stream_k", M=M, N=N, K=K, **e)
+    assert torch.equal(of1, of2) and torch.equal(out1, out2)
+    assert e["f32"] < 2e-5 and e["bf16"] < 4e-3 and e["dgrad"] < 4e-3 and e["vs_plain"] < 2e-6
+    assert relerr(out1.float(), acc + b + r) < 4e-3 and relerr(base_bf.float(), acc + b + r) < 4e-3
+
+
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K", [(256, 64, 64), (4864, 64, 768), (4864, 768, 64), (608, 1536, 512),
                                    (1000, 128, 208), (4608, 768, 512), (4864, 768, 3072)])
