@@ -147,7 +147,7 @@ __device__ __forceinline__ TileRef decode_unit(const Params& p, int v) {
 // Work item `it` of a pair: first its round-robin units over all of K, then (stream-K) its one or two k-block segments
 // of the last round's tiles. Returns false when the pair is done. sk_tile = -1 for ordinary units.
 struct Item { TileRef t; int ka, ke, sk_tile; };
-template <int BN>
+template <int BN, bool SK>
 __device__ __forceinline__ bool get_item(const Params& p, int pair_id, int num_pairs, int total_kb, int it, Item& w) {
   const int u = pair_id + it * num_pairs;
   if (u < p.virt_units) {
@@ -157,7 +157,7 @@ __device__ __forceinline__ bool get_item(const Params& p, int pair_id, int num_p
     w.sk_tile = -1;
     return true;
   }
-  if (p.sk_q == 0) return false;
+  if (!SK) return false;   // the ordinary instantiation is exactly the round-robin loop over units
   const int mine = pair_id < p.virt_units ? (p.virt_units - pair_id + num_pairs - 1) / num_pairs : 0;  // units before
   const int si = it - mine;
   const long long lo = (long long)pair_id * p.sk_q, tot = (long long)p.sk_tiles * total_kb;
@@ -187,7 +187,7 @@ __device__ __forceinline__ bool get_item(const Params& p, int pair_id, int num_p
   return true;
 }
 
-template <int BN, int KIND, int F32>
+template <int BN, int KIND, int F32, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -259,7 +259,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       Item w;
-      for (int it = 0; get_item<BN>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
+      for (int it = 0; get_item<BN, SK>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
         const TileRef t = w.t;
         const int row_a = t.pm * (2 * BM) + (int)rank * BM;
         // a column slice uses the first width / 2 rows of each CTA's B tile (the box always brings BN / 2 rows)
@@ -285,7 +285,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       Item w;
-      for (int it = 0; get_item<BN>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
+      for (int it = 0; get_item<BN, SK>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
         const uint32_t idesc = make_idesc(2 * BM, w.t.width, false, false);
         const int buf = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
@@ -338,14 +338,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const int r = lane;
     uint32_t g = 0;  // chunks processed so far: double-buffered tiles use g & 1, load-barrier parity = (g >> 1) & 1
     Item w;
-    for (int it = 0; get_item<BN>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
+    for (int it = 0; get_item<BN, SK>(p, pair_id, num_pairs, total_kb, it, w); ++it) {
       const TileRef t = w.t;
       const int buf = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = t.pm * (2 * BM) + (int)rank * BM + quarter * 32;
       // stream-K (plain epilogues only): partial accumulators of the pairs sk_first .. pair_id - 1 belong to this tile
       int sk_n = 0, sk_first = 0;
-      if constexpr (KIND == EPK_PLAIN) {
+      if constexpr (SK && KIND == EPK_PLAIN) {
         if (w.sk_tile >= 0 && w.ke < total_kb) {
           // ---- head / middle of a tile: dump the fp32 partial (this warp: its 32 rows x its column half) ----
           mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
@@ -461,7 +461,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tmem_empty0[buf]);
           }
-          if (KIND == EPK_PLAIN && sk_n > 0) {
+          if (SK && KIND == EPK_PLAIN && sk_n > 0) {
 #pragma unroll 1
             for (int sp = 0; sp < sk_n; ++sp) {
               const float4* src = reinterpret_cast<const float4*>(p.sk_ws) +
@@ -572,7 +572,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             v[i] = __uint_as_float(ra[i]);
             v[32 + i] = __uint_as_float(rb[i]);
           }
-          if (KIND == EPK_PLAIN && sk_n > 0) {
+          if (SK && KIND == EPK_PLAIN && sk_n > 0) {
 #pragma unroll 1
             for (int sp = 0; sp < sk_n; ++sp) {
               const float4* src = reinterpret_cast<const float4*>(p.sk_ws) +
@@ -809,11 +809,13 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   if (p.has_z) FV_TRY(make_tmap_2d(&tz, zptr, 2, (uint64_t)N, (uint64_t)M, (uint64_t)N, YW, 32, YSW));
   if (p.has_f32) FV_TRY(make_tmap_2d(&tx, e.out_f32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
   if (p.has_res) FV_TRY(make_tmap_2d(&tr, e.residual, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
-  static bool attr_set = false;
-  if (!attr_set) {
-    FV_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, KIND, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 C::SMEM_BYTES));
-    attr_set = true;
+  constexpr bool CAN_SK = (KIND == EPK_PLAIN);
+  auto kernel = gemm_tc2_kernel<BN, KIND, F32, false>;
+  if (CAN_SK && p.sk_q) kernel = gemm_tc2_kernel<BN, KIND, F32, CAN_SK>;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[p.sk_q ? 1 : 0]) {
+    FV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[p.sk_q ? 1 : 0] = true;
   }
   const int units = p.virt_units;
   const int max_pairs = num_sms() / 2;
@@ -823,8 +825,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
     if (sk_pairs > pairs) pairs = sk_pairs;
   }
   ProfScope prof(0, 2.0 * M * (double)N * K, stream);
-  FV_CUDA(launch_pdl(gemm_tc2_kernel<BN, KIND, F32>, dim3(2 * pairs), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta,
-                     tb, ty, tz, tx, tr, p));
+  FV_CUDA(launch_pdl(kernel, dim3(2 * pairs), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta, tb, ty, tz, tx, tr, p));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
