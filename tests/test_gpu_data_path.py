@@ -255,6 +255,9 @@ def test_expression_aware_vit_step_matches_reference_golden(precision, tol_l, to
     assert e_l < tol_l and abs(loss.item() - float(z["loss"])) < tol_l * 10
     assert errs[worst] < tol_g, (worst, errs[worst])
     assert torch.equal(logits.argmax(-1).cpu(), torch.from_numpy(z["logits"]).argmax(-1))
+    with torch.no_grad():                                         # scores ride along with the same decomposer launch
+        lg2, sc = model.forward_with_scores(torch.from_numpy(z["x"]).cuda())
+    assert torch.equal(lg2, logits.detach()) and relerr(sc, torch.from_numpy(z["scores"])) < 1e-5
 
 
 def test_graphed_mixup_train_step_matches_eager():
