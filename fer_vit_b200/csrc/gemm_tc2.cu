@@ -212,7 +212,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const bool leader = (rank == 0);
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int units = p.virt_units;   // full tiles, then the column slices of the last partial round
   const int total_kb = (p.K + BK - 1) / BK;
 
   pdl_trigger();  // the next kernel may start its own prologue while this one runs
