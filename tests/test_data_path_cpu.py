@@ -170,3 +170,30 @@ def test_decomposer_host_surface():
         d(torch.randn(2, 18, 64), output_mode="nope")
     with pytest.raises(ValueError, match="Unknown mode"):
         d.decompose(torch.randn(2, 18, 64), mode="nope")
+
+
+def test_generator_restatement_matches_the_c_source(tmp_path):
+    """The kernels' counter-based generator (csrc/common.cuh, __host__ __device__) compiled for the HOST and run here:
+    the oracle's numpy mix_hash64 / mix_hash give the same 64- and 32-bit values, and the dropout threshold rounding is
+    the one the oracle's mask replay assumes. Pins the draws of dropout, LatentAugment and mixup without a GPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mix_hash_host")
+    subprocess.run([nvcc, "-O1", "-std=c++17", "--expt-relaxed-constexpr", "-I", os.path.join(root, "fer_vit_b200", "csrc"),
+                    "-I", os.path.join(root, "include"), os.path.join(root, "tests", "host", "mix_hash_host.cu"),
+                    "-o", exe], check=True, capture_output=True, timeout=300)
+    cases = [(0, 0, 0), (42, 3, 17), (0xC0FFEE, 0x4C410000, 123456789), (2 ** 63 + 5, 0x4C410003, 2 ** 40 + 7),
+             (0xFFFFFFFFFFFFFFFF, 0xFFFF1, 0xFFFFFFFF), (1000, 0x4C410002, 31)]
+    args = [str(v) for c in cases for v in c]
+    lines = subprocess.run([exe, *args], check=True, capture_output=True, text=True, timeout=60).stdout.split("\n")
+    for (seed, site, idx), line in zip(cases, lines):
+        h64, h32 = (int(v) for v in line.split())
+        assert int(R.mix_hash64(seed, site, [idx])[0]) == h64, (seed, site, idx)
+        assert int(R.mix_hash(seed, site, [idx])[0]) == h32
+        assert h32 == h64 >> 32
+    thr = [int(v) for v in lines[len(cases)].split()[1:]]
+    assert thr == [int(float(np.float32(p)) * 4294967296.0) for p in (0.1, 0.5, 0.999)]
