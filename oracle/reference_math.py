@@ -304,6 +304,15 @@ def mix_hash(seed: int, site: int, idx):
     return (mix_hash64(seed, site, idx) >> np.uint64(32)).astype(np.uint32)
 
 
+def dropout_keep(seed: int, site: int, idx, p: float):
+    """keep-mask of the kernels' counter-based dropout (common.cuh: drop_keep / drop_threshold): element `idx` of
+    dropout site `site` survives iff the 32-bit mix is >= floor(p * 2^32); survivors are scaled by 1 / (1 - p)."""
+    import numpy as np
+    t = float(np.float32(p)) * 4294967296.0
+    thr = 0 if t <= 0 else (4294967295 if t >= 4294967295.0 else int(t))
+    return torch.from_numpy(mix_hash(seed, site, idx) >= np.uint32(thr))
+
+
 def latent_augment_draws(seed: int, B: int, row: int, scale_range=None, mask_prob: float = 0.0):
     """(normal [B, row] f64, scale [B] f64, keep [B, row] bool) for batch positions 0..B-1 under `seed`, as
     include/fervit_b200.h (fervit_latent_batch) defines them."""

@@ -12,6 +12,15 @@ int main(int argc, char** argv) {
     const unsigned long long idx = strtoull(argv[i + 2], nullptr, 0);
     printf("%llu %u\n", (unsigned long long)fervit::mix_hash64(seed, site, idx), fervit::mix_hash(seed, site, idx));
   }
+  {  // keep-mask of 64 consecutive elements of one dropout site at p = 0.1 and p = 0.5, as bit strings
+    const float ps[2] = {0.1f, 0.5f};
+    for (int k = 0; k < 2; ++k) {
+      printf("K ");
+      for (unsigned long long i = 0; i < 64; ++i)
+        putchar(fervit::drop_keep(12345ull, 9u, 1000ull + i, fervit::drop_threshold(ps[k])) ? '1' : '0');
+      printf("\n");
+    }
+  }
   printf("T %u %u %u\n", fervit::drop_threshold(0.1f), fervit::drop_threshold(0.5f), fervit::drop_threshold(0.999f));
   return 0;
 }

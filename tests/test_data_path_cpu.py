@@ -195,5 +195,8 @@ def test_generator_restatement_matches_the_c_source(tmp_path):
         assert int(R.mix_hash64(seed, site, [idx])[0]) == h64, (seed, site, idx)
         assert int(R.mix_hash(seed, site, [idx])[0]) == h32
         assert h32 == h64 >> 32
-    thr = [int(v) for v in lines[len(cases)].split()[1:]]
+    for line, p in zip(lines[len(cases):len(cases) + 2], (0.1, 0.5)):
+        keep = R.dropout_keep(12345, 9, np.arange(1000, 1064), p)
+        assert line.split()[1] == "".join("1" if k else "0" for k in keep.tolist()), p
+    thr = [int(v) for v in lines[len(cases) + 2].split()[1:]]
     assert thr == [int(float(np.float32(p)) * 4294967296.0) for p in (0.1, 0.5, 0.999)]
