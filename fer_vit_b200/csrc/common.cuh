@@ -133,7 +133,7 @@ __device__ __forceinline__ float gelu_bwd_fast(float u) {
 //   Phi(u)   = 0.5 + uc * P8(uc^2),  uc = clamp(u, -4, 4): |error| <= 7e-6 inside, <= 3.2e-5 in the clamped tails
 //   gelu'(u) = 0.5 + uc * Q9(uc^2):                        |error| <= 6e-5 inside, <= 5.4e-4 in the clamped tails
 // (minimax fits of the exact erf forms; bf16 outputs round at 2^-9 = 2e-3 relative).
-__device__ __forceinline__ float gelu_fwd_poly(float u) {
+__host__ __device__ __forceinline__ float gelu_fwd_poly(float u) {
   const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
   const float s = uc * uc;
   float p = 3.463219783e-01f / 4294967296.0f;                    // coefficients of (s/16)^k, k = 8 .. 0
@@ -167,7 +167,7 @@ __device__ __forceinline__ void gelu_fwd_deriv_poly(float u, float& g, float& d)
   g = u * cdf;
   d = fmaf(u * 0.39894228040143267794f, e, cdf);
 }
-__device__ __forceinline__ float gelu_bwd_poly(float u) {
+__host__ __device__ __forceinline__ float gelu_bwd_poly(float u) {
   const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
   const float s = uc * uc;
   float p = -3.606366035e+00f / 68719476736.0f;                  // (s/16)^k, k = 9 .. 0

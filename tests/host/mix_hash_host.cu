@@ -3,6 +3,7 @@
 // index) triples given on the command line, so the oracle's numpy restatement is pinned on the C source without a GPU.
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include "common.cuh"
 
 int main(int argc, char** argv) {
@@ -20,6 +21,19 @@ int main(int argc, char** argv) {
         putchar(fervit::drop_keep(12345ull, 9u, 1000ull + i, fervit::drop_threshold(ps[k])) ? '1' : '0');
       printf("\n");
     }
+  }
+  {  // worst absolute error of the MUFU-free GELU polynomials of the tensor-core epilogues against the erf forms
+    double e_in = 0, e_tail = 0, d_in = 0, d_tail = 0;
+    for (int i = -80000; i <= 80000; ++i) {
+      const double u = i * 1e-4;
+      const double cdf = 0.5 * (1.0 + erf(u / sqrt(2.0)));
+      const double g = u * cdf, d = cdf + u * exp(-0.5 * u * u) / sqrt(2.0 * 3.14159265358979323846);
+      const double eg = fabs((double)fervit::gelu_fwd_poly((float)u) - g);
+      const double ed = fabs((double)fervit::gelu_bwd_poly((float)u) - d);
+      if (fabs(u) <= 4.0) { if (eg > e_in) e_in = eg; if (ed > d_in) d_in = ed; }
+      else { if (eg > e_tail) e_tail = eg; if (ed > d_tail) d_tail = ed; }
+    }
+    printf("G %.3e %.3e %.3e %.3e\n", e_in, e_tail, d_in, d_tail);
   }
   printf("T %u %u %u\n", fervit::drop_threshold(0.1f), fervit::drop_threshold(0.5f), fervit::drop_threshold(0.999f));
   return 0;

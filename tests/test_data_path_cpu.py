@@ -198,5 +198,9 @@ def test_generator_restatement_matches_the_c_source(tmp_path):
     for line, p in zip(lines[len(cases):len(cases) + 2], (0.1, 0.5)):
         keep = R.dropout_keep(12345, 9, np.arange(1000, 1064), p)
         assert line.split()[1] == "".join("1" if k else "0" for k in keep.tolist()), p
-    thr = [int(v) for v in lines[len(cases) + 2].split()[1:]]
+    # GELU polynomials of the GEMM epilogues vs the exact erf forms on [-8, 8], step 1e-4: the bounds common.cuh states
+    # (absolute; |gelu| error inside the clamp is u * 7e-6 <= 2.8e-5)
+    g_in, g_tail, d_in, d_tail = (float(v) for v in lines[len(cases) + 2].split()[1:])
+    assert g_in < 3e-5 and g_tail < 3e-4 and d_in < 7e-5 and d_tail < 6e-4, (g_in, g_tail, d_in, d_tail)
+    thr = [int(v) for v in lines[len(cases) + 3].split()[1:]]
     assert thr == [int(float(np.float32(p)) * 4294967296.0) for p in (0.1, 0.5, 0.999)]
