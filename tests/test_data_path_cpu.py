@@ -204,3 +204,24 @@ def test_generator_restatement_matches_the_c_source(tmp_path):
     assert g_in < 3e-5 and g_tail < 3e-4 and d_in < 7e-5 and d_tail < 6e-4, (g_in, g_tail, d_in, d_tail)
     thr = [int(v) for v in lines[len(cases) + 3].split()[1:]]
     assert thr == [int(float(np.float32(p)) * 4294967296.0) for p in (0.1, 0.5, 0.999)]
+
+
+def test_stream_k_schedule_invariants(tmp_path):
+    """The stream-K work decomposition the GEMM kernel runs (csrc/gemm_tc2_sched.cuh), replayed on the host for every
+    tile count up to 260 x six K depths x three pair counts: every k-block of every tile exactly once, at most two
+    segments per pair with the head first, one partial (one scratch slot) per pair, and the owner's expected partial
+    count / writer range equal to what the other pairs actually produce - the conditions under which the device
+    protocol is deadlock-free and deterministic."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "streamk_sched_host")
+    subprocess.run([nvcc, "-O1", "-std=c++17", "-I", os.path.join(root, "fer_vit_b200", "csrc"),
+                    os.path.join(root, "tests", "host", "streamk_sched_host.cu"), "-o", exe], check=True,
+                   capture_output=True, timeout=300)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout.strip()
+    assert out.startswith("OK "), out
+    assert int(out.split()[1]) > 500
