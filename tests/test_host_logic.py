@@ -197,3 +197,41 @@ def test_fused_adamw_has_no_cpu_fallback():
     p.grad = torch.randn(4, 4)
     with pytest.raises(RuntimeError, match="CUDA"):
         opt.step()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) runs without a GPU and prints ONE
+    JSON line with the contract's keys: same metric / unit / config as the product arm, impl = reference, a cpu_baseline
+    describing the run and an e2e object repeating the value with zero host<->device bytes."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_committed_launch_summary_matches_its_launch_list():
+    """profiles/: the per-kernel summary of the final step is what tools/ncu_summary.py derives from the committed ncu
+    launch list (the GEMM share of the step quoted in bench.py / DESIGN.md comes from it)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r01_launches_step_final.csv")
+    want = open(os.path.join(root, "profiles", "r01_launches_step_final_summary.txt")).read().strip().splitlines()
+    got = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), csv_path], capture_output=True,
+                         text=True, timeout=120).stdout.strip().splitlines()
+    assert got[0] == want[0]
+    assert got[1:6] == want[1:6]
