@@ -91,6 +91,39 @@ int main() {
         }
         ++cases;
       }
-  printf("OK %d\n", cases);
+  // ---- tail splitting without stream-K: every column of every tile exactly once, slices only in the last round ----
+  int split_cases = 0;
+  for (int mpi = 0; mpi < 3; ++mpi)
+    for (int units = 1; units <= 400; ++units) {
+      const int mp = pair_counts[mpi], kb = 12;
+      Params p;
+      memset(&p, 0, sizeof(p));
+      p.n_blocks = 9;
+      p.pair_m_blocks = (units + 8) / 9;
+      p.full_units = units / mp * mp;
+      const int rest = units - p.full_units;
+      p.split = 1;
+      if (p.full_units > 0 && rest > 0) {            // same rule as tc2::launch (bf16 kinds: slices of >= 64 columns)
+        if (rest * 4 <= mp) p.split = 4;
+        else if (rest * 2 <= mp) p.split = 2;
+      }
+      p.virt_units = p.full_units + rest * p.split;
+      const int pairs = p.virt_units < mp ? p.virt_units : mp;
+      std::vector<int> col((size_t)units * BN, 0);
+      for (int pair = 0; pair < pairs; ++pair) {
+        Item w;
+        for (int it = 0; get_item<BN, false>(p, pair, pairs, kb, it, w); ++it) {
+          const int tile = w.t.pm * p.n_blocks + w.t.n_blk;
+          if (tile >= units || w.ka != 0 || w.ke != kb || w.sk_tile != -1) return fail("bad unit", units, kb, mp, pair);
+          if (w.t.width != BN && tile < p.full_units) return fail("slice outside the last round", units, kb, mp, pair);
+          if (w.t.width * p.split != BN && w.t.width != BN) return fail("slice width", units, kb, mp, pair);
+          for (int c = w.t.col_off; c < w.t.col_off + w.t.width; ++c) col[(size_t)tile * BN + c]++;
+        }
+      }
+      for (size_t i = 0; i < col.size(); ++i)
+        if (col[i] != 1) return fail("column not covered exactly once", units, kb, mp, (int)(i / BN));
+      ++split_cases;
+    }
+  printf("OK %d %d\n", cases, split_cases);
   return 0;
 }

@@ -225,3 +225,4 @@ def test_stream_k_schedule_invariants(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=120).stdout.strip()
     assert out.startswith("OK "), out
     assert int(out.split()[1]) > 500
+    assert int(out.split()[2]) == 1200      # tail splitting (no stream-K): every column of every tile exactly once
