@@ -374,3 +374,27 @@ def decomposer_forward(w_plus: Tensor, directions: Tensor, output_mode: str = "e
     if output_mode == "concat":
         return torch.cat([expr, ident], dim=1)
     raise ValueError(f"Unknown output_mode: {output_mode!r}")
+
+
+# ------------------------------------------------------------------------------------------------
+# Optimizer step of the trainers: clip_grad_norm_ + AdamW (train_latent_vit_v2.py:132-134, :263;
+# train_hybrid_latent_vit.py:244-248)
+# ------------------------------------------------------------------------------------------------
+def clip_grad_norm(grads: Mapping[str, Tensor], max_norm: float):
+    """torch.nn.utils.clip_grad_norm_ (L2): every gradient times min(1, max_norm / (total_norm + 1e-6)).
+    Returns (clipped gradients, total norm)."""
+    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads.values()))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    return {k: g * coef.to(g.dtype) for k, g in grads.items()}, total
+
+
+def adamw_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int, lr: float,
+               betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
+    """One torch.optim.AdamW update (decoupled weight decay, bias correction, amsgrad off) for step number `step`
+    (1-based). Returns (param, exp_avg, exp_avg_sq)."""
+    b1, b2 = betas
+    param = param * (1 - lr * weight_decay)
+    exp_avg = b1 * exp_avg + (1 - b1) * grad
+    exp_avg_sq = b2 * exp_avg_sq + (1 - b2) * grad * grad
+    denom = exp_avg_sq.sqrt() / math.sqrt(1 - b2 ** step) + eps
+    return param - (lr / (1 - b1 ** step)) * exp_avg / denom, exp_avg, exp_avg_sq

@@ -226,3 +226,39 @@ def test_stream_k_schedule_invariants(tmp_path):
     assert out.startswith("OK "), out
     assert int(out.split()[1]) > 500
     assert int(out.split()[2]) == 1200      # tail splitting (no stream-K): every column of every tile exactly once
+
+
+def test_oracle_optimizer_step_matches_reference_trainer_golden():
+    """One batch of the reference's train_latent_vit_v2.train_epoch (mixup, weighted smoothed CE, clip_grad_norm_ active,
+    AdamW): the oracle's forward + mixup loss + gradients + `clip_grad_norm` + `adamw_step` reproduce the loss, the
+    gradient norm and EVERY parameter update of the unmodified trainer."""
+    z = np.load(os.path.join(GOLDEN, "v2_train_epoch.npz"))
+    g = load_golden("latent_vit_v2")
+    after = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("after/")}
+    sd = {k: (v.double().requires_grad_(k in after and k != "spe.groups") if v.is_floating_point() else v)
+          for k, v in g["sd"].items()}
+    x, y, index = torch.from_numpy(z["x"]).double(), torch.from_numpy(z["y"]), torch.from_numpy(z["index"])
+    lam, w = float(z["lam"]), torch.from_numpy(z["class_weight"]).double()
+    logits = R.latent_vit_v2_forward(sd, R.mixup(x, index, lam), 2, 2, True, True, True, True)
+    loss = R.mixup_loss(logits, y, index, lam, w, float(z["label_smoothing"]))
+    assert abs(loss.item() - float(z["loss"])) < 1e-10
+    grads = R.grads_of(loss, sd)
+    clipped, total = R.clip_grad_norm(grads, float(z["grad_clip"]))
+    assert abs(float(total) - float(z["total_norm"])) < 1e-9 and float(total) > float(z["grad_clip"])
+    assert set(clipped) == set(after)
+    for k, gr in clipped.items():
+        p0 = sd[k].detach()
+        p1, m, v = R.adamw_step(p0, gr, torch.zeros_like(p0), torch.zeros_like(p0), 1, float(z["lr"]), (0.9, 0.999), 1e-8,
+                                float(z["weight_decay"]))
+        assert relerr(p1 - p0, after[k] - p0) < 1e-7, k
+    # second step of the restatement against torch's own AdamW (state carried over, no clipping)
+    p = torch.randn(5, 7, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    tp = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([tp], lr=3e-3, betas=(0.8, 0.95), eps=1e-7, weight_decay=0.1)
+    m, v, q = torch.zeros_like(p), torch.zeros_like(p), p.clone()
+    for step in (1, 2, 3):
+        gr = torch.randn(5, 7, dtype=torch.float64, generator=torch.Generator().manual_seed(10 + step))
+        tp.grad = gr.clone()
+        opt.step()
+        q, m, v = R.adamw_step(q, gr, m, v, step, 3e-3, (0.8, 0.95), 1e-7, 0.1)
+        assert relerr(q, tp.detach()) < 1e-14
