@@ -235,3 +235,39 @@ def test_committed_launch_summary_matches_its_launch_list():
                          text=True, timeout=120).stdout.strip().splitlines()
     assert got[0] == want[0]
     assert got[1:6] == want[1:6]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/train"), reason="needs the reference tree (build container only)")
+@pytest.mark.parametrize("frozen,adapter", [(True, True), (False, True), (False, False)])
+def test_reference_optimizer_grouping_runs_on_the_drop_in_model(frozen, adapter):
+    """The reference trainer's OWN `get_optimizer_groups` (train/train_hybrid_latent_vit.py:63-117), imported unmodified,
+    applied to the drop-in HybridLatentViT: it finds input_proj / transformer / adapters / head / pos_embed + cls_token
+    exactly as on the reference model (same groups, same parameter counts, same learning rates), and the groups feed
+    FusedAdamW's per-group hyper-parameter table."""
+    import importlib
+    import sys
+    import fer_vit_b200 as fv
+    from fer_vit_b200.models_fer_vit.vit_blocks import register_vit_config
+    from oracle import timm_shim
+    timm_shim.install()
+    for pth in ("/root/reference", "/root/reference/train"):
+        if pth not in sys.path:
+            sys.path.insert(0, pth)
+    tr = importlib.import_module("train.train_hybrid_latent_vit")
+    assert tr.__file__.startswith("/root/reference")
+    register_vit_config("vit_test_patch16_224", 64, 2, 2)
+    kw = dict(latent_dim=64, seq_len=18, pretrained_model_name="vit_test_patch16_224", num_classes=7,
+              use_pretrained=False, freeze_transformer=frozen, adapter_dim=16 if adapter else None)
+    ours = fv.HybridLatentViT(verbose=False, **kw)
+    ref = tr.HybridLatentViT(**kw)
+    g_ours = tr.get_optimizer_groups(ours, 1e-4, 0.01)
+    g_ref = tr.get_optimizer_groups(ref, 1e-4, 0.01)
+    assert len(g_ours) == len(g_ref) == (3 + (0 if frozen else 1) + (1 if adapter else 0))
+    for a, b in zip(g_ours, g_ref):
+        assert a["lr"] == b["lr"] and a["weight_decay"] == b["weight_decay"]
+        assert [tuple(p.shape) for p in a["params"]] == [tuple(p.shape) for p in b["params"]]
+        # the reference builds the input-projection and head groups from .parameters() without a requires_grad filter
+        assert [p.requires_grad for p in a["params"]] == [p.requires_grad for p in b["params"]]
+    opt = fv.FusedAdamW(g_ours, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0)
+    assert [r[0] for r in opt._hyper_rows()] == [g["lr"] for g in g_ref]
+    assert opt._hyper_rows()[-1][4] == 0.0          # pos_embed / cls_token: no weight decay
