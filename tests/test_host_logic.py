@@ -271,3 +271,39 @@ def test_reference_optimizer_grouping_runs_on_the_drop_in_model(frozen, adapter)
     opt = fv.FusedAdamW(g_ours, lr=1e-4, weight_decay=0.01, max_grad_norm=1.0)
     assert [r[0] for r in opt._hyper_rows()] == [g["lr"] for g in g_ref]
     assert opt._hyper_rows()[-1][4] == 0.0          # pos_embed / cls_token: no weight decay
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models_fer_vit"), reason="needs the reference tree")
+@pytest.mark.parametrize("output_mode", ["expr_only", "concat"])
+def test_expression_aware_factory_matches_the_reference(tmp_path, output_mode):
+    """ExpressionAwareViT.from_config on a directions file (the format compute_expression_directions.py writes), beside
+    the unmodified reference factory: same token count ('concat' doubles it), same state_dict keys and shapes, same
+    trainable-parameter list, same normalised directions."""
+    import importlib
+    import sys
+    import fer_vit_b200 as fv
+    from oracle import timm_shim
+    timm_shim.install()
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    ref_mod = importlib.import_module("models_fer_vit.expression_aware_vit")
+    assert ref_mod.__file__.startswith("/root/reference")
+    g = torch.Generator().manual_seed(4)
+    path = str(tmp_path / "binary_directions.pt")
+    torch.save({"directions": {i: torch.randn(18, 512, generator=g) for i in range(7)}, "seq_len": 18, "latent_dim": 512,
+                "method": "binary"}, path)
+    kw = dict(model_size="tiny", num_classes=7, use_pretrained=False, freeze_transformer=True, use_adapter=True,
+              adapter_dim=8, output_mode=output_mode, enhance_alpha=1.5, decompose_mode="max_class")
+    ours = fv.ExpressionAwareViT.from_config(path, **kw)
+    ref = ref_mod.ExpressionAwareViT.from_config(path, **kw)
+    assert ours.vit.seq_len == ref.vit.seq_len == (36 if output_mode == "concat" else 18)
+    assert (ours.output_mode, ours.enhance_alpha, ours.decompose_mode) == (ref.output_mode, ref.enhance_alpha,
+                                                                           ref.decompose_mode)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert list(so) == list(sr)
+    assert all(so[k].shape == sr[k].shape and so[k].dtype == sr[k].dtype for k in so)
+    assert torch.allclose(so["decomposer.directions"], sr["decomposer.directions"], atol=1e-7)
+    assert [tuple(p.shape) for p in ours.get_trainable_params()] == [tuple(p.shape) for p in ref.get_trainable_params()]
+    ref.load_state_dict(so, strict=True)            # a checkpoint of the drop-in loads into the reference, and back
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    ours.print_info()
