@@ -142,8 +142,10 @@ class PackedLatentCache:
         self.transform = transform
         self.status = torch.zeros(1, dtype=torch.int32, device=self.latents.device)
 
-    @classmethod
-    def from_dir(cls, latent_dir: str, transform: Optional[LatentAugment] = None, device="cuda"):
+    @staticmethod
+    def read_dir(latent_dir: str):
+        """(latents [N, 18, 512] float32, labels [N] int64) on the host: every ``*.pt`` of the directory in the
+        reference dataset's order (sorted file names), read once."""
         if not os.path.exists(latent_dir):
             raise FileNotFoundError(f"Latent directory not found: {latent_dir}")
         files = [os.path.join(latent_dir, f) for f in sorted(os.listdir(latent_dir)) if f.endswith(".pt")]
@@ -157,8 +159,14 @@ class PackedLatentCache:
                 lab.append(int(d["label"]))
             except Exception as e:  # same contract as the reference __getitem__
                 raise RuntimeError(f"Error loading {fp}: {e}")
-        host = torch.stack(lat).pin_memory() if torch.cuda.is_available() else torch.stack(lat)
-        return cls(host, torch.tensor(lab, dtype=torch.int64), transform, device)
+        return torch.stack(lat), torch.tensor(lab, dtype=torch.int64)
+
+    @classmethod
+    def from_dir(cls, latent_dir: str, transform: Optional[LatentAugment] = None, device="cuda"):
+        host, labels = cls.read_dir(latent_dir)
+        if torch.cuda.is_available():
+            host = host.pin_memory()
+        return cls(host, labels, transform, device)
 
     def __len__(self) -> int:
         return self.latents.shape[0]

@@ -262,3 +262,37 @@ def test_oracle_optimizer_step_matches_reference_trainer_golden():
         opt.step()
         q, m, v = R.adamw_step(q, gr, m, v, step, 3e-3, (0.8, 0.95), 1e-7, 0.1)
         assert relerr(q, tp.detach()) < 1e-14
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="needs the reference tree")
+def test_packed_cache_reads_a_directory_like_the_reference_dataset(tmp_path):
+    """PackedLatentCache.read_dir (the host half of from_dir) beside the unmodified LatentFERDataset on the same
+    directory of per-sample .pt files: same order (sorted names, non-.pt files ignored), same latents and labels, same
+    class counts; a corrupt file raises the reference's RuntimeError."""
+    import importlib
+    import sys
+    import fer_vit_b200 as fv
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    ds_mod = importlib.import_module("data.latent_dataset")
+    assert ds_mod.__file__.startswith("/root/reference")
+    g = torch.Generator().manual_seed(6)
+    names = ["img_0010.pt", "img_0002.pt", "zz.pt", "a_first.pt", "img_0001.pt"]
+    for i, n in enumerate(names):
+        torch.save({"latent": torch.randn(18, 512, generator=g), "label": int(i * 3 % 7), "img_path": n + ".png"},
+                   tmp_path / n)
+    (tmp_path / "notes.txt").write_text("not a latent")
+    ref = ds_mod.LatentFERDataset(str(tmp_path))
+    lat, lab = fv.PackedLatentCache.read_dir(str(tmp_path))
+    assert len(ref) == lat.shape[0] == len(names)
+    for i in range(len(ref)):
+        x, y = ref[i]
+        assert torch.equal(lat[i], x) and int(lab[i]) == y
+    counts = {int(v): int(c) for v, c in zip(*torch.unique(lab, return_counts=True))}
+    assert counts == ref.get_class_counts()
+    assert fv.PackedLatentCache.CLASS_NAMES == ref.get_class_names()
+    (tmp_path / "broken.pt").write_bytes(b"not a checkpoint")
+    with pytest.raises(RuntimeError, match="Error loading"):
+        fv.PackedLatentCache.read_dir(str(tmp_path))
+    with pytest.raises(RuntimeError, match="Error loading"):
+        ds_mod.LatentFERDataset(str(tmp_path))[1]          # 'broken.pt' sorts second
