@@ -296,3 +296,28 @@ def test_packed_cache_reads_a_directory_like_the_reference_dataset(tmp_path):
         fv.PackedLatentCache.read_dir(str(tmp_path))
     with pytest.raises(RuntimeError, match="Error loading"):
         ds_mod.LatentFERDataset(str(tmp_path))[1]          # 'broken.pt' sorts second
+
+
+def test_oracle_hybrid_trainer_step_matches_reference_golden():
+    """The headline configuration's whole optimizer step as the reference trainer runs it
+    (train_hybrid_latent_vit.train_epoch in train mode: head Dropout(0.1) with the mask torch drew; AdamW over the
+    trainer's own get_optimizer_groups - lr x10 / x10 / x10 / x5, no decay on pos_embed + cls_token; frozen blocks):
+    the oracle reproduces the loss, the train accuracy and every trainable tensor's update."""
+    z = np.load(os.path.join(GOLDEN, "hybrid_train_epoch.npz"))
+    g = load_golden("hybrid_adapter")
+    hyper = {k[6:]: tuple(float(v) for v in z[k]) for k in z.files if k.startswith("hyper/")}
+    assert len(hyper) == 18 and not any(k.startswith("transformer.") for k in hyper)
+    assert hyper["pos_embed"] == (5e-4, 0.0) and hyper["head.2.weight"] == (1e-3, 0.01)
+    assert hyper["adapters.0.alpha"] == (1e-3, 0.01) and hyper["input_proj.weight"] == (1e-3, 0.01)
+    sd = {k: (v.double().requires_grad_(k in hyper) if v.is_floating_point() else v) for k, v in g["sd"].items()}
+    y = torch.from_numpy(z["y"])
+    logits = R.hybrid_forward(sd, torch.from_numpy(z["x"]).double(), 2, 2, True,
+                              {"head": torch.from_numpy(z["head_mask"])})
+    loss = R.cross_entropy(logits, y)
+    assert abs(loss.item() - float(z["loss"])) < 1e-10
+    assert abs((logits.argmax(-1) == y).double().mean().item() - float(z["accuracy"])) < 1e-12
+    grads = R.grads_of(loss, sd)
+    for k, (lr, wd) in hyper.items():
+        p0 = sd[k].detach()
+        p1, _, _ = R.adamw_step(p0, grads[k], torch.zeros_like(p0), torch.zeros_like(p0), 1, lr, (0.9, 0.999), 1e-8, wd)
+        assert relerr(p1 - p0, torch.from_numpy(z["after/" + k]) - p0) < 1e-7, k
