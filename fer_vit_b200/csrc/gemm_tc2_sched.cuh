@@ -32,9 +32,9 @@ struct Params {
   // MMA time) and pays ~6 us for dumping and re-reading 128 KB of partials per CTA, the re-read sitting on the
   // epilogue's critical path. (A row-major scratch layout cost 21 us: 16-byte accesses at a 1 KB stride; the
   // lane-interleaved one is coalesced.) It is therefore opt-in - a caller-provided scratch, or FERVIT_GEMM_STREAMK=1
-  // for the plans - until the owner pre-loads the partial into its TMEM accumulator (tcgen05.st) while the head
-  // segment's MMAs run, which takes the fix-up off the critical path. It also gives up batch invariance of the
-  // results (the summation order then depends on the tile count).
+  // for the plans - until the owner prefetches the partial chunks into shared-memory staging (cp.async) before it
+  // waits for its accumulator, which takes the re-read off the critical path ("next" 1). It also gives up
+  // batch invariance of the results (the summation order then depends on the tile count).
   int sk_q, sk_tiles;
   float* sk_ws;   // [pairs][2][BM][BN] fp32
   int* sk_flags;  // [sk_tiles][2] arrival counters, zero between launches
