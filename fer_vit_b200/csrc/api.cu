@@ -102,7 +102,8 @@ FV_API int fervit_linear_forward(int act_dtype, const void* x, const void* W, co
                                  void* pre, int force_bn, void* stream) {
   FV_CHECK(x && W, "linear_forward: null argument");
   Epilogue e = make_epilogue();
-  e.bias = bias; e.residual = residual; e.act = act; e.out = out; e.out_f32 = out_f32; e.out_pre = pre; e.ldo = N;
+  e.bias = bias; e.residual = residual; e.act = act & 0xff; e.out = out; e.out_f32 = out_f32; e.out_pre = pre; e.ldo = N;
+  e.pre_is_deriv = (act & 0x100) ? 1 : 0;
   if (act_dtype == FERVIT_F32)
     return gemm_f32_simt((const float*)x, K, 1, (const float*)W, K, 1, M, N, K, 1, e, S_(stream));
   FV_CHECK(act_dtype == FERVIT_BF16, "linear_forward: unknown dtype %d", act_dtype);
@@ -145,6 +146,11 @@ FV_API int fervit_set_gemm_scratch(void* ptr, long long bytes) { return gemm_tc2
 FV_API int fervit_debug_gemm_clock(double* ns, double* cycles) {
   FV_CHECK(ns && cycles, "debug_gemm_clock: null argument");
   return gemm_tc2_clock_probe(ns, cycles);
+}
+
+FV_API int fervit_debug_gemm_timeline(unsigned long long* out, int n) {
+  FV_CHECK(out, "debug_gemm_timeline: null argument");
+  return gemm_tc2_timeline(out, n);
 }
 
 FV_API int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const void* aux, const float* residual,

@@ -89,6 +89,12 @@ struct Cfg {
 
 // [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
 __device__ unsigned long long g_clock_probe[4];
+// debug bit 64: clock64 stamps of the phases of two CTAs (row 0: CTA 0, row 1: leader of the last pair); slots in TL_*
+constexpr int TL_N = 32;
+__device__ unsigned long long g_timeline[2][TL_N];
+enum { TL_ENTRY = 0, TL_PROLOGUE = 1, TL_GRIDSYNC = 2, TL_FIRST_FULL = 3, TL_MMA_ISSUED = 4 /* +it, it < 4 */,
+       TL_TMA_FIRST = 8, TL_TMA_LAST = 9, TL_ACC_READY = 10 /* +2*it */, TL_EPI_DONE = 11 /* +2*it */,
+       TL_STORES_READ = 18, TL_FINAL_SYNC = 19, TL_END = 20, TL_EPI7_DONE = 21 /* +it */, TL_GT0 = 30, TL_GT1 = 31 };
 
 template <int BN, int KIND, int F32, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -117,7 +123,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int num_pairs = gridDim.x >> 1;
   const int total_kb = (p.K + BK - 1) / BK;
 
+  const int tl_row = (p.debug & 64) ? (blockIdx.x == 0 ? 0 : (blockIdx.x == gridDim.x - 2 ? 1 : -1)) : -1;
+  auto TL = [&](int slot) {
+    if (tl_row >= 0) g_timeline[tl_row][slot] = (unsigned long long)clock64();
+  };
   pdl_trigger();  // the next kernel may start its own prologue while this one runs
+  if (tl_row >= 0 && threadIdx.x == 0) {
+    TL(TL_ENTRY);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline[tl_row][TL_GT0] = t;
+  }
   if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -152,8 +168,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) TL(TL_PROLOGUE);
   // everything above is independent of the previous kernel's output (PDL): wait for it only now
   pdl_grid_sync();
+  if (threadIdx.x == 0) TL(TL_GRIDSYNC);
 
   if (warp == W_TMA) {
     // ===================== TMA producer (both CTAs) =====================
@@ -177,6 +195,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           const uint32_t full0 = mapa(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tm_a, full0, kb * BK, row_a);
           tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tm_b, full0, kb * BK, row_b);
+          if (it == 0 && kb == w.ka) TL(TL_TMA_FIRST);
+          TL(TL_TMA_LAST);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -197,6 +217,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int kb = w.ka; kb < ((p.debug & 3) == 3 ? w.ka : w.ke); ++kb) {
           mbar_wait_parked(&full_bar[stage], phase, 3);
           tc_fence_after();
+          if (it == 0 && kb == w.ka) TL(TL_FIRST_FULL);
           if (p.debug & 2) {
             mbar_arrive(&empty_bar[stage]);
             mbar_arrive_cluster(mapa(smem_u32(&empty_bar[stage]), 1));
@@ -215,6 +236,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           umma_commit_pair(&empty_bar[stage], 3);  // frees the slot in both CTAs once these MMAs have read it
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        if (it < 4) TL(TL_MMA_ISSUED + it);
         if (p.debug & 2) {
           mbar_arrive(&tmem_full[buf]);
           mbar_arrive_cluster(mapa(smem_u32(&tmem_full[buf]), 1));
@@ -331,6 +353,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
         tc_fence_after();
+        if (ew == 0 && lane == 0 && it < 4) TL(TL_ACC_READY + 2 * it);
         if (C::ALIAS && res && lane == 0 && nch > 0) {
           // single-tile form: the staging tiles alias the operand ring, free now that every MMA has completed
           for (int jj = 0; jj < nch && jj < (int)XB; ++jj) issue_load(g + jj, col0 + jj * CW);
@@ -442,6 +465,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         }
         mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
         tc_fence_after();
+        if (ew == 0 && lane == 0 && it < 4) TL(TL_ACC_READY + 2 * it);
         if (nch == 0) {
           tc_fence_before();
           __syncwarp();
@@ -578,15 +602,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
         }
       }
+      if (lane == 0 && it < 4) {
+        if (ew == 0) TL(TL_EPI_DONE + 2 * it);
+        if (ew == EPI_WARPS - 1) TL(TL_EPI7_DONE + it);
+      }
     }
     // the staging tiles must outlive their last readers; global visibility comes with grid completion
     if (lane == 0) tma_store_wait_read<0>();
+    if (ew == 0 && lane == 0) TL(TL_STORES_READ);
   }
 
   tc_fence_before();
   cluster_sync();
   tc_fence_after();
+  if (threadIdx.x == 0) TL(TL_FINAL_SYNC);
   if (warp == W_ALLOC) tmem_dealloc<2>(tmem_base, (uint32_t)C::TMEM_COLS);
+  if (tl_row >= 0 && threadIdx.x == 0) {
+    TL(TL_END);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_timeline[tl_row][TL_GT1] = t;
+  }
   if ((p.debug & 8) && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -753,6 +789,13 @@ int gemm_tc2_clock_probe(double* ns, double* cycles) {
   FV_CUDA(cudaMemcpyFromSymbol(h, tc2::g_clock_probe, sizeof(h)));
   *ns = (double)(h[1] - h[0]);
   *cycles = (double)(h[3] - h[2]);
+  return 0;
+}
+
+// diagnostics (FERVIT_GEMM_DEBUG bit 64): phase stamps of two CTAs of the last CTA-pair GEMM, 2 x 32 values
+int gemm_tc2_timeline(unsigned long long* out, int n) {
+  FV_CHECK(n >= 2 * tc2::TL_N, "gemm timeline: need room for %d values", 2 * tc2::TL_N);
+  FV_CUDA(cudaMemcpyFromSymbol(out, tc2::g_timeline, sizeof(unsigned long long) * 2 * tc2::TL_N));
   return 0;
 }
 

@@ -250,7 +250,8 @@ int fervit_premodules_backward(const fervit_premodules* p, const float* x, const
 
 /* y = act(x W^T + b) (+ residual): nn.Linear / F.linear. fp32 mode: x, W fp32; bf16 mode: x, W bf16 ([N,K]).
  * out (act_dtype) and out_f32 may each be NULL; residual fp32 [M,N] may be NULL; pre (act_dtype, pre-activation) may
- * be NULL. force_bn (ignored in fp32 mode): 0 = auto; 128 / 256 = N tile of the CTA-pair tcgen05 kernel; -64 / -128 /
+ * be NULL; act | 0x100 makes `pre` receive act'(pre-activation) instead (what the plan saves for the backward GEMM).
+ * force_bn (ignored in fp32 mode): 0 = auto; 128 / 256 = N tile of the CTA-pair tcgen05 kernel; -64 / -128 /
  * -256 = force the single-CTA tcgen05 kernel with that N tile (benchmarks and tests). */
 int fervit_linear_forward(int act_dtype, const void* x, const void* W, const float* bias, const float* residual,
                           int M, int N, int K, int act, void* out, float* out_f32, void* pre, int force_bn,
@@ -328,6 +329,10 @@ int fervit_set_gemm_scratch(void* ptr, long long bytes);
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 8 set, the CTA-pair GEMM records the wall time (ns, %globaltimer) and the SM
  * cycle count (clock64) of its CTA 0; cycles / ns = the SM clock in GHz while the kernel ran. */
 int fervit_debug_gemm_clock(double* ns, double* cycles);
+
+/* Diagnostics: with FERVIT_GEMM_DEBUG bit 64 set, the CTA-pair GEMM stamps clock64 at every phase boundary of two CTAs
+ * (row 0: CTA 0, row 1: leader of the last pair); out receives 2 x 32 values (slot meanings: csrc/gemm_tc2.cu TL_*). */
+int fervit_debug_gemm_timeline(unsigned long long* out, int n);
 
 /* fp32 -> bf16 cast (n multiple of 4) */
 int fervit_cast_bf16(const float* src, void* dst, long long n, void* stream);

@@ -1,0 +1,101 @@
+"""Phase timeline of the CTA-pair tcgen05 GEMM (FERVIT_GEMM_DEBUG bit 64): where a launch spends its time.
+
+    python tools/gemm_timeline.py [--shapes qkv,proj,fc1,fc2,fc2_dgrad] [--m 4864]
+
+For each batch-256 shape of the ViT-B block the kernel stamps clock64 at its phase boundaries in two CTAs (CTA 0 and
+the leader of the last pair); the table below is in microseconds from kernel entry (SM clock from %globaltimer).
+Results of the GEMM are unaffected by the stamps; timings are of one warm launch with operands resident in L2, the
+situation inside the train step.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+os.environ["FERVIT_GEMM_DEBUG"] = "64"
+
+import torch  # noqa: E402
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from fer_vit_b200 import _lib as L  # noqa: E402
+
+SLOTS = {0: "entry", 1: "prologue done", 2: "grid dependency", 3: "first operands landed", 8: "first TMA issued",
+         9: "last TMA issued", 18: "stores drained", 19: "final cluster sync", 20: "end"}
+for it in range(4):
+    SLOTS[4 + it] = f"MMAs of item {it} issued"
+    SLOTS[10 + 2 * it] = f"accumulator {it} ready (warp 0)"
+    SLOTS[11 + 2 * it] = f"epilogue {it} done (warp 0)"
+    SLOTS[21 + it] = f"epilogue {it} done (warp 7)"
+
+
+def shapes(M):
+    E, F = 768, 3072
+    return {
+        "qkv": dict(N=3 * E, K=E, bias=True),
+        "proj": dict(N=E, K=E, bias=True, residual=True, out_f32=True),
+        "fc1": dict(N=F, K=E, bias=True, act=2 | 0x100),
+        "fc2": dict(N=E, K=F, bias=True, residual=True, out_f32=True),
+        "fc2_dgrad": dict(N=F, K=E, mul_bwd=True),
+        "fc1_dgrad": dict(N=E, K=F),
+        "qkv_dgrad": dict(N=E, K=3 * E),
+    }
+
+
+def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd=False, iters=5):
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    W = torch.randn(N, K, device="cuda").bfloat16()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    of = torch.empty(M, N, device="cuda") if out_f32 else None
+    b = torch.randn(N, device="cuda") if bias else None
+    r = torch.randn(M, N, device="cuda") if residual else None
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16) if act else None
+    aux = torch.randn(M, N, device="cuda").bfloat16() if mul_bwd else None
+    st = torch.cuda.current_stream().cuda_stream
+    p = lambda t: t.data_ptr() if t is not None else None
+    lib = L.lib()
+
+    def launch():
+        if mul_bwd:
+            # dX = dY W (transposed weight [K_in = N here]) with the saved derivative multiplied in
+            L.check(lib.fervit_linear_dgrad(L.BF16, x.data_ptr(), W.data_ptr(), p(aux), None, M, K, N, 3,
+                                            out.data_ptr(), None, 0, st))   # reduction over K (API name: N)
+        else:
+            L.check(lib.fervit_linear_forward(L.BF16, x.data_ptr(), W.data_ptr(), p(b), p(r), M, N, K, act,
+                                              None if out_f32 else out.data_ptr(), p(of), p(pre), 0, st))
+    ev = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); launch(); e1.record()
+        torch.cuda.synchronize()
+        ev.append(e0.elapsed_time(e1) * 1e3)
+    buf = (ctypes.c_ulonglong * 64)()
+    L.check(lib.fervit_debug_gemm_timeline(buf, 64))
+    rows = []
+    for row in range(2):
+        t = list(buf[row * 32:(row + 1) * 32])
+        cyc = t[20] - t[0]
+        ns = t[31] - t[30]
+        ghz = cyc / max(ns, 1)
+        rec = {"cta": "first" if row == 0 else "last pair", "kernel_us": round(ns / 1e3, 2), "sm_ghz": round(ghz, 3)}
+        for s, nm in sorted(SLOTS.items()):
+            if t[s] >= t[0] and t[s] != 0 and t[s] <= t[20] + 10:
+                rec[nm] = round((t[s] - t[0]) / ghz / 1e3, 2)
+        rows.append(rec)
+    return {"gemm": name, "M": M, "N": N, "K": K, "event_us_median": round(sorted(ev)[len(ev) // 2], 1), "ctas": rows}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shapes", default="qkv,proj,fc1,fc2,fc2_dgrad,fc1_dgrad")
+    ap.add_argument("--m", type=int, default=4864)
+    a = ap.parse_args()
+    sh = shapes(a.m)
+    for name in a.shapes.split(","):
+        kw = dict(sh[name])
+        N, K = kw.pop("N"), kw.pop("K")
+        print(json.dumps(run(name, a.m, N, K, **kw)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
