@@ -75,6 +75,7 @@ SIGNATURES = {
     "fervit_plan_forward": (_i, [_p, _p, _i, _p, _ll, _i, _i, _u64, _p, _p, _p]),
     "fervit_plan_num_stages": (_i, [_p]),
     "fervit_plan_backward": (_i, [_p, _p, _i, _p, _ll, _i, _u64, _p, _p, C.POINTER(_p), _i, _i, _i, _p]),
+    "fervit_plan_saved_buffer": (_i, [_p, _p, _i, _i, _i, C.POINTER(_p), C.POINTER(_ll)]),
     "fervit_cross_entropy": (_i, [_p, _p, _p, _f, _i, _i, _p, _f, _p, _p, _p, _p]),
     "fervit_cross_entropy_mixup": (_i, [_p, _p, _p, _p, _f, _i, _i, _f, _p, _f, _p, _p, _p]),
     "fervit_latent_batch": (_i, [_p, _p, _ll, _p, _i, _ll, C.POINTER(LatentAugmentParams), _u64, _p, _p, C.c_double, _p, _p,

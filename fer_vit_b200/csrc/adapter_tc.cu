@@ -334,7 +334,7 @@ int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, 
   }
   const int grid = ceil_div(T, adp::BM) * p.groups;
   // FLOPs of the two contractions (phase 1 counted once, as the GEMM pair it replaces)
-  ProfScope prof(0, 4.0 * T * (double)E * adp::AD, stream);
+  ProfScope prof(5, 4.0 * T * (double)E * adp::AD, stream);
   FV_CUDA(launch_pdl(adp::adapter_kernel, dim3(grid), dim3(adp::THREADS), (size_t)adp::SMEM_BYTES, stream, t_in, t_aw, t_bw,
                      t_res, t_out, t_outb, p));
   FV_COUNT_LAUNCH();

@@ -15,7 +15,7 @@ FV_API const char* fervit_last_error(void) { return get_error(); }
 FV_API unsigned long long fervit_launch_count(void) { return g_launch_count; }
 
 FV_API int fervit_profile_enable(int on) {
-  prof_enable(on != 0);
+  prof_enable(on);
   return 0;
 }
 FV_API int fervit_profile_read(int kernel_class, double* ms, double* work, long long* launches) {

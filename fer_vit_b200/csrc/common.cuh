@@ -76,9 +76,10 @@ __device__ __forceinline__ void pdl_grid_sync() { asm volatile("griddepcontrol.w
 // per-kernel-class event timing (runtime.cu); classes: 0 tcgen05 GEMM (flops), 1 attention (bytes),
 // 2 LayerNorm (bytes), 3 fp32 GEMM (flops)
 bool prof_enabled();
+bool prof_serial();
 int prof_open(int cls, double work, cudaStream_t st);
 void prof_close(int id, cudaStream_t st);
-void prof_enable(bool on);
+void prof_enable(int mode);
 int prof_read(int cls, double* ms, double* work, long long* count);
 struct ProfScope {
   int id; cudaStream_t st;

@@ -432,7 +432,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, const Params& 
   const int m_blocks = ceil_div(p.M, BM), n_blocks = ceil_div(p.N, BN);
   const int units = m_blocks * n_blocks * p.splits;
   const int grid = units < num_sms() ? units : num_sms();
-  ProfScope prof(0, 2.0 * p.M * (double)p.N * p.K, stream);
+  ProfScope prof(4, 2.0 * p.M * (double)p.N * p.K, stream);
   FV_CUDA(launch_pdl(gemm_tc_kernel<BN, A_MN, B_MN, KIND>, dim3(grid), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta,
                      tb, p));
   FV_COUNT_LAUNCH();

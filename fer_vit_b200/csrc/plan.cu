@@ -375,7 +375,7 @@ int ensure_side_stream(fervit_plan* p) {
 bool use_side_stream() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("FERVIT_SIDE_STREAM"); on = (e && atoi(e) == 0) ? 0 : 1; }
-  return on == 1 && !prof_enabled();   // the per-kernel event profile wants one serial stream
+  return on == 1 && !prof_serial();   // the per-kernel event profile wants one serial stream
 }
 
 PreParams pre_params(const fervit_plan* p) {
@@ -952,6 +952,24 @@ FV_API int fervit_plan_forward(fervit_plan* plan, const float* x, int B, void* w
 }
 
 FV_API int fervit_plan_num_stages(const fervit_plan* plan) { return plan ? plan->cfg.depth + 2 : 0; }
+
+FV_API int fervit_plan_saved_buffer(const fervit_plan* plan, void* ws, int B, int block, int which, void** ptr,
+                                    long long* numel) {
+  FV_CHECK(plan && ws && ptr && numel, "saved_buffer: null argument");
+  FV_CHECK(B > 0 && block >= 0 && block < plan->cfg.depth, "saved_buffer: bad batch or block");
+  Arena ar{reinterpret_cast<char*>(ws), 0};
+  Bufs b;
+  if (plan->cfg.mode == FERVIT_BF16) carve<bf16>(plan, B, true, ar, b);
+  else carve<float>(plan, B, true, ar, b);
+  const long long T = (long long)B * plan->S;
+  switch (which) {
+    case FERVIT_SAVED_ACT_DERIV: *ptr = b.blk[block].u1; *numel = T * plan->cfg.F; break;
+    case FERVIT_SAVED_ACT_OUT: *ptr = b.blk[block].g1; *numel = T * plan->cfg.F; break;
+    case FERVIT_SAVED_QKV: *ptr = b.blk[block].qkv; *numel = T * 3 * plan->cfg.E; break;
+    default: FV_CHECK(false, "saved_buffer: unknown buffer id %d", which);
+  }
+  return 0;
+}
 
 FV_API int fervit_plan_backward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
                                 unsigned long long seed, const unsigned long long* seed_dev, const float* dlogits,

@@ -39,7 +39,8 @@ int num_sms() {
 // Off by default; never enabled inside a timed region or a graph capture.
 // ---------------------------------------------------------------------------------------------
 struct ProfRec { cudaEvent_t a, b; int cls; double work; };
-static bool g_prof_on = false;
+static bool g_prof_on = false;      // record per-launch events
+static bool g_prof_serial = false;  // keep the backward on one stream (no side branch) without recording anything
 static std::vector<ProfRec> g_prof;
 
 // Events come from a pool created when profiling is switched on: creating two events per launch on the hot host path
@@ -49,6 +50,7 @@ static size_t g_pool_next = 0;
 constexpr size_t PROF_POOL = 8192;
 
 bool prof_enabled() { return g_prof_on; }
+bool prof_serial() { return g_prof_on || g_prof_serial; }
 int prof_open(int cls, double work, cudaStream_t st) {
   if (g_pool_next + 2 > g_pool.size()) return -1;   // pool exhausted: stop recording rather than stall the host
   ProfRec r;
@@ -62,7 +64,9 @@ int prof_open(int cls, double work, cudaStream_t st) {
 void prof_close(int id, cudaStream_t st) {
   if (id >= 0 && id < (int)g_prof.size()) cudaEventRecord(g_prof[id].b, st);
 }
-void prof_enable(bool on) {
+void prof_enable(int mode) {   // 0 off, 1 per-launch events (serial), 2 serial only
+  const bool on = mode == 1;
+  g_prof_serial = mode == 2;
   g_prof.clear();
   g_pool_next = 0;
   if (on && g_pool.empty()) {

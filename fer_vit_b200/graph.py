@@ -72,7 +72,21 @@ class GraphedTrainStep:
         self.optimizer.step()
         return loss.detach()
 
+    def close(self) -> None:
+        """Release the captured graph. Required before ``torch.distributed.destroy_process_group()`` when the step
+        was captured under ``enable_data_parallel``: a live graph keeps the captured NCCL collectives (and with them
+        the communicator) alive, and ``ncclCommDestroy`` then blocks."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
+    def _check_open(self) -> None:
+        if self.graph is None:
+            raise RuntimeError("fer_vit_b200: this graphed train step has been closed")
+
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self._check_open()
         if x.shape != self.static_x.shape or y.shape != self.static_y.shape:
             raise RuntimeError(f"fer_vit_b200: GraphedTrainStep was captured for {tuple(self.static_x.shape)} / "
                                f"{tuple(self.static_y.shape)}, got {tuple(x.shape)} / {tuple(y.shape)}")
@@ -130,6 +144,7 @@ class GraphedMixupTrainStep(GraphedTrainStep):
         return loss.detach()
 
     def __call__(self, sample_idx: torch.Tensor, mix_index: torch.Tensor, lam: float):
+        self._check_open()
         if sample_idx.shape != self.static_idx.shape or mix_index.shape != self.static_mix.shape:
             raise RuntimeError(f"fer_vit_b200: GraphedMixupTrainStep was captured for batches of "
                                f"{self.static_idx.numel()}, got {sample_idx.numel()} / {mix_index.numel()}")

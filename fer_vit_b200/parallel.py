@@ -8,7 +8,8 @@ The native backward writes all gradients of a step into ONE flat fp32 buffer lai
 (head | block 11 ... block 0 | input stage), so a bucket is a contiguous slice. The backward is cut into
 `num_buckets` stage groups; the all-reduce of a finished bucket is launched asynchronously (NCCL's own stream) while
 the next group of blocks is still computing, and the compute stream waits for the buckets only after the last
-group. At this payload the collective is latency-bound (tens of microseconds), so 2 buckets is the default.
+group. At this payload the collective is latency-bound (tens of microseconds); 3 buckets is the default, cut so
+that only the input stage's 1.6 MB is exposed after the backward pass (`GradBucketer.stage_groups`).
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ import torch.distributed as dist
 class GradBucketer:
     """Overlapped, bucketed gradient averaging for runtime.PlanRunner.backward()."""
 
-    def __init__(self, process_group: Optional[dist.ProcessGroup] = None, num_buckets: int = 2):
+    def __init__(self, process_group: Optional[dist.ProcessGroup] = None, num_buckets: int = 3):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = process_group
@@ -34,10 +35,22 @@ class GradBucketer:
         self.calls = 0
 
     def stage_groups(self, nstages: int) -> List[Tuple[int, int]]:
-        """Contiguous stage ranges [b, e), one per bucket; the head and the latest blocks come first."""
+        """Contiguous stage ranges [b, e), one per bucket; the head and the latest blocks come first.
+
+        The all-reduce of a bucket overlaps only the stages that run AFTER it, so the cuts are made from the end: the
+        last bucket is the input stage alone (its collective is fully exposed whatever it holds: keep it to the token
+        projection's 1.6 MB), the bucket before it the two earliest blocks (its collective hides behind the input
+        stage), and the remaining buckets split the head and the later blocks evenly."""
         n = min(self.num_buckets, nstages)
-        cuts = [round(i * nstages / n) for i in range(n + 1)]
-        return [(cuts[i], cuts[i + 1]) for i in range(n) if cuts[i + 1] > cuts[i]]
+        if n <= 1:
+            return [(0, nstages)]
+        if n == 2:
+            cuts = [0, nstages - 1, nstages]
+        else:
+            tail = max(1, nstages - 3)
+            head = [round(i * tail / (n - 2)) for i in range(n - 1)]
+            cuts = head + [nstages - 1, nstages]
+        return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
 
     def reduce_async(self, flat: torch.Tensor) -> None:
         op = dist.ReduceOp.AVG if self._native_avg else dist.ReduceOp.SUM
@@ -62,7 +75,7 @@ def sync_parameters(model: torch.nn.Module, src: int = 0, process_group=None) ->
             dist.broadcast(t, src=src, group=process_group)
 
 
-def enable_data_parallel(model, process_group=None, num_buckets: int = 2, broadcast: bool = True) -> GradBucketer:
+def enable_data_parallel(model, process_group=None, num_buckets: int = 3, broadcast: bool = True) -> GradBucketer:
     """Attach overlapped gradient averaging to a fer_vit_b200 model (any NativeModule)."""
     if broadcast:
         sync_parameters(model, 0, process_group)

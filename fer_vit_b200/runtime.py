@@ -15,6 +15,24 @@ from . import _lib as L
 
 _GEMM_BLOCK_SLOTS = (L.B_QKV_W, L.B_PROJ_W, L.B_FC1_W, L.B_FC2_W, L.B_AD1_W, L.B_AD2_W)
 
+# Parameter gradients the native backward produces TOGETHER (one kernel sequence writes all members: plan.cu keys each
+# weight/bias pair on the weight's pointer, the adapter and head groups on one member, the pre-modules on their flags).
+# A drop-in nn.Module must honour per-parameter requires_grad, so a request for any member is widened to the whole
+# group on the native side and the extra gradients are dropped before they reach autograd.
+_BLOCK_GRAD_GROUPS = ((L.B_LN1_W, L.B_LN1_B), (L.B_QKV_W, L.B_QKV_B), (L.B_PROJ_W, L.B_PROJ_B), (L.B_LN2_W, L.B_LN2_B),
+                      (L.B_FC1_W, L.B_FC1_B), (L.B_FC2_W, L.B_FC2_B),
+                      (L.B_AD1_W, L.B_AD1_B, L.B_AD2_W, L.B_AD2_B, L.B_ALPHA))
+_GLOBAL_GRAD_GROUPS = ((L.G_HEAD_LN_W, L.G_HEAD_LN_B, L.G_HEAD_W, L.G_HEAD_B), (L.G_IN_W, L.G_IN_B),
+                       (L.G_SPE_GROUP, L.G_SPE_LAYER, L.G_LWN_GAMMA, L.G_LWN_BETA, L.G_LWN_GATE, L.G_LEAM_W))
+
+
+def grad_groups(depth: int):
+    """Every group of parameter slots whose gradients the native backward computes together."""
+    groups = [tuple(g) for g in _GLOBAL_GRAD_GROUPS]
+    for b in range(depth):
+        groups += [tuple(L.bslot(b, s) for s in g) for g in _BLOCK_GRAD_GROUPS]
+    return groups
+
 
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -48,6 +66,9 @@ class PlanRunner:
         self.seed_dev: Optional[torch.Tensor] = None  # device uint64 counter for CUDA-graph replays
         self._seed_calls = 0
         self.grad_sync = None  # optional parallel.GradBucketer
+        self.keep_workspace = False   # tests: keep the last saved-for-backward workspace alive (saved_activation)
+        self.last_ws: Optional[torch.Tensor] = None
+        self.last_batch = 0
         # gradient layout in backward order: head, blocks depth-1..0, input stage
         head = [L.G_HEAD_LN_W, L.G_HEAD_LN_B, L.G_HEAD_W, L.G_HEAD_B]
         inp = [L.G_IN_W, L.G_IN_B, L.G_CLS, L.G_POS, L.G_SPE_GROUP, L.G_SPE_LAYER, L.G_LWN_GAMMA, L.G_LWN_BETA,
@@ -150,7 +171,24 @@ class PlanRunner:
         L.check(self._lib.fervit_plan_forward(self._h, x.data_ptr(), B, ws.data_ptr(), ws.numel(),
                                               1 if training else 0, 1 if save else 0, seed, sd, logits.data_ptr(),
                                               _stream_ptr()))
+        if save and self.keep_workspace:
+            self.last_ws, self.last_batch = ws, B
         return logits, ws, seed, x
+
+    def saved_activation(self, block: int, which: int = 0) -> torch.Tensor:
+        """A per-block activation of the last forward that saved for backward (needs ``keep_workspace = True`` before
+        that forward): ``which`` 0 = act'(fc1 pre-activation) — for ReLU the 0/1 active set —, 1 = the activation,
+        2 = qkv. Returned as a float32 copy [B*S, width]."""
+        if self.last_ws is None:
+            raise RuntimeError("fer_vit_b200: set plan_runner().keep_workspace = True before the forward pass")
+        ptr, n = C.c_void_p(), C.c_longlong()
+        L.check(self._lib.fervit_plan_saved_buffer(self._h, self.last_ws.data_ptr(), self.last_batch, block, which,
+                                                   C.byref(ptr), C.byref(n)))
+        esize = 2 if self.bf16 else 4
+        off = ptr.value - self.last_ws.data_ptr()
+        raw = self.last_ws[off:off + n.value * esize]
+        t = raw.view(torch.bfloat16 if self.bf16 else torch.float32).float()
+        return t.reshape(self.last_batch * (self.cfg.L + 1), -1)
 
     def backward(self, x: torch.Tensor, ws: torch.Tensor, training: bool, seed: int, dlogits: torch.Tensor,
                  want: Dict[int, torch.Size]) -> Dict[int, torch.Tensor]:
@@ -167,7 +205,8 @@ class PlanRunner:
                     offsets[s] = off
                     off += (want[s].numel() + 63) // 64 * 64
             stage_ranges.append((begin, off))
-        flat = torch.empty(max(off, 1), dtype=torch.float32, device=x.device)
+        # zero-filled: a slot the native code did not write must read as "no gradient", never as stale memory
+        flat = torch.zeros(max(off, 1), dtype=torch.float32, device=x.device)
         base = flat.data_ptr()
         ptrs = [None] * self.nslots
         for s, o in offsets.items():
@@ -218,7 +257,13 @@ class _PlanFunction(torch.autograd.Function):
             raise NotImplementedError("fer_vit_b200: gradient with respect to the model input is not implemented "
                                       "(the reference train step never requests it)")
         need = ctx.needs_input_grad[5:]
-        want = {s: shp for s, shp, n in zip(ctx.slots, ctx.shapes, need) if n and s != L.G_SPE_GROUPS}
+        shapes = dict(zip(ctx.slots, ctx.shapes))
+        asked = {s for s, n in zip(ctx.slots, need) if n and s != L.G_SPE_GROUPS}
+        native = set(asked)
+        for grp in grad_groups(ctx.runner.depth):     # per-parameter requires_grad: widen to what is computed together
+            if native.intersection(grp):
+                native.update(s for s in grp if s in shapes)
+        want = {s: shapes[s] for s in native}
         grads = ctx.runner.backward(x, ctx.ws, ctx.training, ctx.seed, dlogits, want)
         ctx.ws = None
         out = [grads.get(s) if n else None for s, n in zip(ctx.slots, need)]

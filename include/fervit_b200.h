@@ -31,9 +31,12 @@ const char* fervit_last_error(void);
 unsigned long long fervit_launch_count(void);
 
 /* Per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline leg; never on inside a
- * timed region or a graph capture). Classes: 0 tcgen05 GEMM (work = FLOPs), 1 attention (algorithmic bytes),
- * 2 LayerNorm (algorithmic bytes), 3 fp32 CUDA-core GEMM (FLOPs). enable(1) clears earlier records; read() sums the
- * records of one class: total device milliseconds, total work, launch count. */
+ * timed region or a graph capture). Classes: 0 CTA-pair tcgen05 GEMM (work = FLOPs), 1 attention (algorithmic
+ * bytes), 2 LayerNorm (algorithmic bytes), 3 fp32 CUDA-core GEMM (FLOPs), 4 single-CTA tcgen05 GEMM (weight gradients,
+ * token projection; FLOPs), 5 fused AdapterModule kernel (FLOPs of its two contractions). enable(1) clears earlier
+ * records and starts recording; enable(2) records nothing but keeps the backward pass on one stream (no side branch),
+ * the launch order the per-launch records belong to; enable(0) switches both off. read() sums the records of one
+ * class: total device milliseconds, total work, launch count. */
 int fervit_profile_enable(int on);
 int fervit_profile_read(int kernel_class, double* ms, double* work, long long* launches);
 
@@ -155,6 +158,17 @@ int fervit_plan_num_stages(const fervit_plan* plan);
 int fervit_plan_backward(fervit_plan* plan, const float* x, int B, void* ws, long long ws_bytes, int training,
                          unsigned long long seed, const unsigned long long* seed_dev, const float* dlogits,
                          float* const* grads, int n, int stage_begin, int stage_end, void* stream);
+
+/* Where a forward pass that saved for backward left one of its per-block activations inside the caller's workspace
+ * `ws` (the same B as that forward). Parity tests read the activation SELECTOR of the MLP from here: with ReLU the
+ * saved derivative is the 0/1 active set the kernel actually used, which the oracle is then given (like a dropout
+ * mask), so that the continuous arithmetic is compared on the same selector. Buffers are in the plan's activation
+ * dtype (bf16 mode: bf16; fp32 mode: float). */
+enum { FERVIT_SAVED_ACT_DERIV = 0,  /* act'(fc1 pre-activation)  [B*S, F] */
+       FERVIT_SAVED_ACT_OUT = 1,    /* act(fc1 pre-activation) after dropout [B*S, F] */
+       FERVIT_SAVED_QKV = 2 };      /* [B*S, 3E] */
+int fervit_plan_saved_buffer(const fervit_plan* plan, void* ws, int B, int block, int which, void** ptr,
+                             long long* numel);
 
 /* ----------------------------------------------------------------------------------------------
  * Loss: nn.CrossEntropyLoss(weight, label_smoothing), mean reduction

@@ -110,7 +110,18 @@ def torch_encoder_layer(x: Tensor, sd: Mapping[str, Tensor], prefix: str, heads:
     a = attention(x, sd[prefix + "self_attn.in_proj_weight"], sd[prefix + "self_attn.in_proj_bias"],
                   sd[prefix + "self_attn.out_proj.weight"], sd[prefix + "self_attn.out_proj.bias"], heads, masks, blk)
     x = layer_norm(x + _mask(a, masks, ("drop1", blk)), sd[prefix + "norm1.weight"], sd[prefix + "norm1.bias"], eps)
-    h = _mask(act(linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])), masks, ("ffn", blk))
+    u = linear(x, sd[prefix + "linear1.weight"], sd[prefix + "linear1.bias"])
+    if masks is not None and "trace" in masks:
+        masks["trace"][("ffn_pre", blk)] = u.detach()
+    if masks is not None and ("relu", blk) in masks:
+        # ReLU with an INJECTED active set (0/1, the one the implementation under test used): relu(u) = u * [u > 0] is
+        # a selector times a linear map, and the selector is discontinuous exactly like a dropout mask — a unit whose
+        # pre-activation is within round-off of zero may legitimately fall on either side. Given the selector, value
+        # and gradient are the reference's (d relu / du = the selector).
+        h = u * masks[("relu", blk)].to(u.dtype)
+    else:
+        h = act(u)
+    h = _mask(h, masks, ("ffn", blk))
     f = _mask(linear(h, sd[prefix + "linear2.weight"], sd[prefix + "linear2.bias"]), masks, ("drop2", blk))
     return layer_norm(x + f, sd[prefix + "norm2.weight"], sd[prefix + "norm2.bias"], eps)
 

@@ -82,15 +82,10 @@ def _global_err(grads, ref):
     return float((a - b).norm() / b.norm())
 
 
-def _compare(tag, precision, got, ref, extra=None, baseline=None, relu=False):
-    """Gates: logits < tol; every gradient tensor < tol; the whole gradient vector < tol.
-
-    relu=True (LatentViT, nn.TransformerEncoderLayer's default activation): the ReLU derivative is discontinuous, so ONE
-    pre-activation whose sign differs between two correct implementations (|u| below round-off) moves a linear1
-    gradient tensor by ~1/sqrt(T*F) ~ 1e-3 regardless of precision. There the per-tensor gate is 10 x tol and the 1x
-    gate applies to the whole gradient vector. In bf16 mode many near-zero pre-activations flip in ANY bf16
-    implementation; `baseline` = torch's own bf16 autocast run of the same parameters, and the gates become
-    max(gate, 1.5 x torch's error)."""
+def _compare(tag, precision, got, ref, extra=None, baseline=None):
+    """Gates (BASELINE.json north_star, un-widened): logits < tol; EVERY gradient tensor < tol; the whole gradient
+    vector < tol; tol = 1e-4 (fp32 mode) / 2e-2 (bf16 mode). `baseline` (torch's own bf16 autocast run of the same
+    parameters) is recorded for information only and gates nothing."""
     logits, loss, grads = got
     rl, rloss, rg = ref
     assert set(grads) == set(rg)
@@ -99,27 +94,67 @@ def _compare(tag, precision, got, ref, extra=None, baseline=None, relu=False):
     errs = {k: relerr(grads[k], rg[k]) for k in rg}
     e_glob = _global_err(grads, rg)
     tol = TOL[precision]
-    tols = {k: (10 * tol if relu else tol) for k in rg}
-    tol_glob = tol
     rec = {}
     if baseline is not None:
         bg = _group(baseline[2])
         berr = {k: relerr(bg[k], rg[k]) for k in rg}
-        tols = {k: max(tols[k], 1.5 * berr[k]) for k in rg}
-        b_glob = _global_err(bg, rg)
-        tol_glob = max(tol, 1.5 * b_glob)
         rec = {"torch_autocast_err_logits": relerr(baseline[0], rl), "torch_autocast_worst_grad": max(berr.values()),
-               "torch_autocast_global_grad": b_glob}
-    worst = max(errs, key=lambda k: errs[k] / tols[k])
+               "torch_autocast_global_grad": _global_err(bg, rg)}
+    worst = max(errs, key=errs.get)
     record(tag, precision=precision, err_logits=e_l, err_loss=abs(loss.item() - rloss.item()), worst_grad=errs[worst],
            worst_key=worst, global_grad=e_glob, **rec, **(extra or {}))
     assert e_l < tol, e_l
-    assert errs[worst] < tols[worst], (worst, errs[worst], tols[worst])
-    assert e_glob < tol_glob, (e_glob, tol_glob)
+    assert errs[worst] < tol, (worst, errs[worst], tol)
+    assert e_glob < tol, (e_glob, tol)
     # top-1 must agree wherever the reference's top-2 margin exceeds the logit tolerance
     top2 = rl.float().topk(2, dim=-1).values
     clear = (top2[:, 0] - top2[:, 1]) > 4 * tol * rl.abs().max()
     assert torch.equal(logits.argmax(-1).cpu()[clear], rl.argmax(-1)[clear])
+
+
+# ReLU models (LatentViT: nn.TransformerEncoderLayer's default activation, latent_vit.py:24-31). relu(u) = u * [u > 0]:
+# a 0/1 SELECTOR times a linear map. The selector is discontinuous in u exactly like a dropout mask is in its random
+# draw: a unit whose pre-activation lies within round-off of zero legitimately falls on either side, and one flipped
+# unit moves a linear1 gradient by O(1/sqrt(T*F)) whatever the precision of everything else (bf16 operands flip
+# ~0.3 % of the units; torch's own bf16 autocast shows the same 3-6e-2 gradient error against an fp64 reference).
+# So, as for dropout, the oracle is handed the selector the kernels actually used (read back from the saved forward
+# state through the C ABI, fervit_plan_saved_buffer) and the PLAIN gates apply to everything else; separately the
+# selector itself is checked against the oracle's own: it may differ only where |u_ref| is within the precision mode's
+# round-off of zero (SEL_BAND x rms(u_ref)), and only on a small fraction of the units.
+SEL_BAND = {"fp32": 2e-4, "bf16": 1e-1}
+SEL_FRAC = {"fp32": 1e-4, "bf16": 2e-2}
+
+
+def _relu_selectors(model, depth, B, S):
+    r = model.plan_runner()
+    return {("relu", i): r.saved_activation(i, 0).reshape(B, S, -1).cpu().double() for i in range(depth)}
+
+
+def _check_selectors(tag, precision, sel, trace):
+    frac, band = 0.0, 0.0
+    for (name, i), m in sel.items():
+        u = trace[("ffn_pre", i)].double()
+        ref = (u > 0).double()
+        flips = m != ref
+        frac = max(frac, float(flips.double().mean()))
+        if flips.any():
+            band = max(band, float(u[flips].abs().max() / u.pow(2).mean().sqrt()))
+    record(tag + "_relu_selector", precision=precision, worst_layer_flip_fraction=frac, worst_flip_abs_u_over_rms=band)
+    assert frac < SEL_FRAC[precision], frac
+    assert band < SEL_BAND[precision], band
+
+
+def _relu_reference(tag, precision, fwd, sd, x, y, sel, masks=None, weight=None, smoothing=0.0):
+    """fp64 oracle step with the kernels' ReLU selectors injected (+ any dropout masks), after checking those
+    selectors against the oracle's own pre-activations."""
+    free = dict(masks or {})
+    free["trace"] = {}
+    with torch.no_grad():
+        fwd({k: (v.detach().double() if v.is_floating_point() else v) for k, v in sd.items()}, x.double(), free)
+    _check_selectors(tag, precision, sel, free["trace"])
+    given = dict(masks or {})
+    given.update(sel)
+    return _oracle_step(fwd, sd, x, y, given, weight, smoothing)
 
 
 def _torch_autocast_step(model, x, y, smoothing=0.0, pre=None):
@@ -208,16 +243,19 @@ def test_latent_vit_default_config_vs_oracle(precision):
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(42)
     x = torch.randn(32, 18, 512, generator=g); y = torch.randint(0, 7, (32,), generator=g)
-    ref = _oracle_step(lambda s, xx, m: R.latent_vit_forward(s, xx, 6, 8, m), sd, x, y, smoothing=0.1)
     model = model.cuda().train()
+    model.plan_runner().keep_workspace = True
     import fer_vit_b200 as fv2
     model.zero_grad(set_to_none=True)
     logits = model(x.cuda())
     loss = fv2.cross_entropy(logits, y.cuda(), None, 0.1)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    sel = _relu_selectors(model, 6, 32, 19)
+    ref = _relu_reference("latent_vit_cfg1", precision, lambda s, xx, m: R.latent_vit_forward(s, xx, 6, 8, m), sd, x, y,
+                          sel, smoothing=0.1)
     base = _torch_autocast_step(model, x.cuda(), y.cuda(), 0.1) if precision == "bf16" else None
-    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref, baseline=base, relu=True)
+    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref, baseline=base)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -235,8 +273,10 @@ def test_latent_vit_dropout_masks_vs_oracle(precision):
     model = model.cuda().train()
     runner = model.plan_runner()
     runner._next_seed = lambda training: 99
+    runner.keep_workspace = True
     x = torch.randn(B, 18, 64); y = torch.randint(0, 7, (B,))
     got = step(model, x.cuda(), y.cuda())
+    sel = _relu_selectors(model, depth, B, S)
 
     def mask(n, site, shape):
         m = torch.empty(n, device="cuda")
@@ -248,8 +288,9 @@ def test_latent_vit_dropout_masks_vs_oracle(precision):
         masks[("drop1", i)] = mask(B * S * E, 8 * i + 1, (B, S, E))
         masks[("ffn", i)] = mask(B * S * F, 8 * i + 2, (B, S, F))
         masks[("drop2", i)] = mask(B * S * E, 8 * i + 3, (B, S, E))
-    ref = _oracle_step(lambda s, xx, m: R.latent_vit_forward(s, xx, depth, H, m), sd, x.double(), y, masks)
-    _compare("latent_vit_dropout", precision, got, ref, relu=True)
+    ref = _relu_reference("latent_vit_dropout", precision, lambda s, xx, m: R.latent_vit_forward(s, xx, depth, H, m),
+                          sd, x.double(), y, sel, masks)
+    _compare("latent_vit_dropout", precision, got, ref)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -270,14 +311,17 @@ def test_latent_vit_v2_config4_vs_oracle(precision):
     g = torch.Generator().manual_seed(43)
     B = 16
     x = 0.6 * torch.randn(B, 18, 512, generator=g) + 0.2; y = torch.randint(0, 7, (B,), generator=g)
-    ref = _oracle_step(lambda s, xx, m: R.latent_vit_v2_forward(s, xx, 6, 8, True, True, True, True, m), sd, x, y)
     model = model.cuda().train()
+    model.plan_runner().keep_workspace = True
     got = step(model, x.cuda(), y.cuda())
+    sel = _relu_selectors(model, 6, B, 19)
+    ref = _relu_reference("latent_vit_v2_cfg4", precision,
+                          lambda s, xx, m: R.latent_vit_v2_forward(s, xx, 6, 8, True, True, True, True, m), sd, x, y, sel)
     base = None
     if precision == "bf16":
         base = _torch_autocast_step(model, x.cuda(), y.cuda(), 0.0,
                                     pre=lambda t: model.leam(model.lwn(model.spe(t))))
-    _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref, baseline=base, relu=True)
+    _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref, baseline=base)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

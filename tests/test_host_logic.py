@@ -208,7 +208,7 @@ def test_bench_reference_arm_contract():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+                        "--warmup", "1", "--batch", "32"], capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1

@@ -67,3 +67,23 @@ def test_post_norm_layer_restatement_matches_torch_layer():
         sd = {"l." + k: v for k, v in lay.state_dict().items()}
         x = torch.randn(3, 19, E, dtype=torch.float64)
         assert relerr(R.torch_encoder_layer(x, sd, "l.", H, act), lay(x)) < 1e-12
+
+
+def test_relu_selector_injection_is_the_reference_relu():
+    """The oracle's injected ReLU active set (parity tests hand it the selector the kernels used): with the oracle's OWN
+    selector it is the plain ReLU path bit for bit, value and gradients; with one unit flipped it differs."""
+    from oracle import reference_math as R
+    g = load_golden("latent_vit")
+    sd = {k: v.double().requires_grad_(True) for k, v in g["sd"].items()}
+    x, y = g["x"].double(), g["y"]
+    masks = {"trace": {}}
+    ref = R.latent_vit_forward(sd, x, 2, 2, masks)
+    gref = R.grads_of(R.cross_entropy(ref, y, g["class_weight"], g["label_smoothing"]), sd)
+    sel = {("relu", i): (masks["trace"][("ffn_pre", i)] > 0).double() for i in range(2)}
+    out = R.latent_vit_forward(sd, x, 2, 2, sel)
+    gout = R.grads_of(R.cross_entropy(out, y, g["class_weight"], g["label_smoothing"]), sd)
+    assert torch.equal(out, ref)
+    assert all(torch.equal(gout[k], gref[k]) for k in gref)
+    flipped = {k: v.clone() for k, v in sel.items()}
+    flipped[("relu", 0)][0, 0, 0] = 1.0 - flipped[("relu", 0)][0, 0, 0]
+    assert not torch.equal(R.latent_vit_forward(sd, x, 2, 2, flipped), ref)
