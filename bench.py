@@ -355,15 +355,78 @@ def main():
     h2d = B * math.prod(shape) * 4 + B * 8
     loss_last = float(host_loss[(args.steps - 1) % host_loss.numel()])
 
-    # ---------------- roofline leg: per-launch CUDA events on the launching stream ----------------
-    # The timed region replays a graph (PDL edges, a parallel backward branch): per-kernel events cannot sit inside it
-    # without breaking those edges. So the SAME kernels are launched once more from the host, in graph order on one
-    # stream, behind a spin kernel long enough for the host to enqueue the whole pass ahead of the GPU: the kernels then
-    # run back to back (no launch gaps inside the event intervals) with warm caches, serialised like an ncu launch
-    # list. `serial_ms_per_step` is the same pass timed WITHOUT per-launch events; shares are fractions of it.
+    # ---------------- roofline leg ----------------
+    # Dominant kernel (the CTA-pair tcgen05 GEMM): timed WHERE IT RUNS, inside a replay of the step's CUDA graph. Events
+    # cannot sit inside the graph without cutting its PDL edges and parallel branch, so the kernel stamps itself:
+    # every launch records {first CTA start after its grid dependency resolved, last CTA exit} in %globaltimer ns
+    # (fervit_gemm_prof; the graph is captured once more with the timer on). Sum of those = the GEMMs' share of the very
+    # step `value` measures. The other classes (attention, LayerNorm, single-CTA GEMM, adapter) are timed with CUDA
+    # events around every launch of a host-launched pass queued behind a spin kernel (back to back, one stream).
     pk = peaks()
     lib = L.lib()
     roof, hbm, classes = None, {}, {}
+    st_ptr = torch.cuda.current_stream().cuda_stream
+    if graphed is not None and args.precision == "bf16":
+        L.check(lib.fervit_gemm_prof(1, None))
+        prof_graph = fv.GraphedTrainStep(model, opt, pool_x[0], pool_y[0])
+        L.check(lib.fervit_gemm_prof(0, None))
+        live_graphs.append(prof_graph)
+        reps, cap = 5, 512
+        tot_us = tot_fl = tot_ms = 0.0
+        nl = 0
+        by_shape = {}
+        kinds = {0: "plain", 1: "gelu", 2: "relu", 3: "gelu'", 4: "relu'", 5: "x saved act'"}
+        for i in range(reps + 1):
+            L.check(lib.fervit_gemm_prof(2, st_ptr))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            prof_graph(pool_x[i % n_pool], pool_y[i % n_pool])
+            e1.record()
+            torch.cuda.synchronize()
+            us, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+            rec = (ctypes.c_double * (6 * cap))()
+            L.check(lib.fervit_gemm_prof_read(ctypes.byref(us), ctypes.byref(fl), ctypes.byref(n), rec, cap))
+            if i == 0:
+                continue
+            tot_us += us.value; tot_fl += fl.value; tot_ms += e0.elapsed_time(e1); nl = n.value
+            for j in range(min(n.value, cap)):
+                d, f, M_, N_, K_, kd = rec[6 * j:6 * j + 6]
+                key = (int(M_), int(N_), int(K_), int(kd))
+                a = by_shape.setdefault(key, [0.0, 0.0, 0])
+                a[0] += d; a[1] += f; a[2] += 1
+        if nl:
+            achieved = tot_fl / (tot_us * 1e-6) / 1e12
+            traffic, traffic_note = None, None
+            tpath = os.path.join(ROOT, "profiles", "r02_ncu_gemm_traffic.json")
+            if not os.path.exists(tpath):
+                tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
+            if os.path.exists(tpath) and args.config == "hybrid":
+                tj = json.load(open(tpath))
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch ({tj['launch']}) from the "
+                                f"committed ncu --set full capture {os.path.basename(tpath)}; algorithmic bytes "
+                                f"{tj['algorithmic_bytes_per_launch']}; {tj['note']}")
+            shapes = []
+            for (M_, N_, K_, kd), (d, f, c) in sorted(by_shape.items(), key=lambda kv: -kv[1][0]):
+                shapes.append({"M": M_, "N": N_, "K": K_, "epilogue": kinds.get(kd % 16, str(kd % 16)) +
+                               (" + fp32 residual stream" if kd >= 16 else ""), "launches_per_step": c // reps,
+                               "avg_us": d / c, "tflops": f / (d * 1e-6) / 1e12,
+                               "frac_of_peak": f / (d * 1e-6) / 1e12 / pk["tflops_sustained"]})
+            roof = {"bound": "tensor", "kernel": "tc2::gemm_tc2_kernel (CTA-pair tcgen05.mma cta_group::2 kind::f16, "
+                                                 "TMA-fed, TMEM accumulators, TMA-store epilogue: every forward / dgrad GEMM)",
+                    "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tflops_sustained"], "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                    "launches_per_step": nl, "flops_per_step": tot_fl / reps,
+                    "avg_launch_us": tot_us / reps / nl, "ms_per_step_in_kernel": tot_us / reps / 1e3,
+                    "share_of_step": (tot_us / reps / 1e3) / (tot_ms / reps), "step_ms_of_timed_replays": tot_ms / reps,
+                    "by_shape": shapes,
+                    "how": "in-kernel %globaltimer stamps (min start after the grid dependency, max exit over the CTAs "
+                           "of each launch) collected from " + str(reps) + " replays of the step's CUDA graph captured "
+                           "with the timer on; share_of_step = sum of the launch durations / the replay's own duration "
+                           "(CUDA events around the replay). Compare with the kernel's share in the ncu launch list "
+                           "under profiles/."}
     psteps = 3
     blocker = int(0.045 * 1.9e9)   # ~45 ms of spin: one host-launched step takes the host ~5-8 ms to enqueue
 
@@ -381,66 +444,47 @@ def main():
         return e0.elapsed_time(e1) / psteps
 
     serial_ms = serial_pass(2)
-    lib.fervit_profile_enable(1)
-    torch.cuda._sleep(blocker)
-    for i in range(psteps):
-        eager_step(pool_x[i % n_pool], pool_y[i % n_pool])
-    torch.cuda.synchronize()
+    serial_pass(1)
 
     def read(cls):
         a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         L.check(lib.fervit_profile_read(cls, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         return a.value / psteps, b.value / psteps, c.value // psteps
-    names = {0: "tc2::gemm_tc2_kernel (CTA-pair tcgen05 GEMM: forward / dgrad)", 4: "tc::gemm_tc_kernel (single-CTA "
-             "tcgen05 GEMM: weight gradients, token projection)", 5: "adp::adapter_kernel (fused AdapterModule)",
-             3: "gemm_simt_kernel (fp32 mode)", 1: "attention", 2: "layernorm"}
+    names = {0: "tc2::gemm_tc2_kernel", 4: "tc::gemm_tc_kernel (single-CTA tcgen05 GEMM: weight gradients, token "
+             "projection)", 5: "adp::adapter_kernel (fused AdapterModule)", 3: "gemm_simt_kernel (fp32 mode)",
+             1: "attention", 2: "layernorm"}
     for cls, nm in names.items():
         t_ms, work, n = read(cls)
         if n:
             classes[cls] = {"kernel": nm, "ms_per_step": t_ms, "launches_per_step": n, "work_per_step": work,
                             "share_of_serial_step": t_ms / serial_ms}
     lib.fervit_profile_enable(0)
-    dom = 0 if 0 in classes else (3 if 3 in classes else None)
-    if dom is not None:
-        c0 = classes[dom]
+    if roof is None and (0 in classes or 3 in classes):   # fp32 mode / --no-graph: event-timed fall-back
+        c0 = classes[0 if 0 in classes else 3]
         achieved = c0["work_per_step"] / (c0["ms_per_step"] * 1e-3) / 1e12
-        traffic, traffic_note = None, None
-        tpath = os.path.join(ROOT, "profiles", "r02_ncu_gemm_traffic.json")
-        if not os.path.exists(tpath):
-            tpath = os.path.join(ROOT, "profiles", "r01_ncu_gemm_traffic.json")
-        if os.path.exists(tpath) and args.config == "hybrid" and dom == 0:
-            tj = json.load(open(tpath))
-            traffic = tj["dram_bytes_per_launch"]
-            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch ({tj['launch']}) from the "
-                            f"committed ncu --set full capture {os.path.basename(tpath)}; algorithmic bytes "
-                            f"{tj['algorithmic_bytes_per_launch']}; {tj['note']}")
-        roof = {"bound": "tensor", "kernel": c0["kernel"], "achieved": achieved, "peak": pk["tflops_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"], "traffic": traffic,
-                "traffic_note": traffic_note,
-                "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
-                "launches_per_step": c0["launches_per_step"], "flops_per_step": c0["work_per_step"],
+        roof = {"bound": "tensor" if 0 in classes else "fp32 CUDA cores", "kernel": c0["kernel"], "achieved": achieved,
+                "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
+                "traffic": None, "launches_per_step": c0["launches_per_step"],
                 "avg_launch_us": c0["ms_per_step"] * 1e3 / c0["launches_per_step"],
-                "ms_per_step_in_kernel": c0["ms_per_step"],
-                "share_of_step": c0["share_of_serial_step"],
-                "serial_ms_per_step": serial_ms,
-                "how": "CUDA events around every launch of a host-launched pass queued behind a spin kernel (back to "
-                       "back, warm caches, one stream); share_of_step = this kernel's time / the same pass timed "
-                       "without per-launch events — compare with the kernel's share in the ncu launch list under "
-                       "profiles/. The graph-replayed step (ms_per_step) is shorter than the serial pass: PDL overlaps "
-                       "prologues and the adapter weight gradients run on a parallel branch."}
-        for cls in (4, 5):
+                "ms_per_step_in_kernel": c0["ms_per_step"], "share_of_step": c0["share_of_serial_step"],
+                "how": "CUDA events around every launch of a host-launched serial pass"}
+    if roof is not None:
+        roof["serial_pass"] = {"ms_per_step": serial_ms, "how": "the same kernels launched from the host on one stream "
+                               "behind a spin kernel, CUDA events around every launch (serialised, warm caches, "
+                               "~2-4 us of event overhead inside every interval): the other kernel classes"}
+        for cls in (0, 4, 5):
             if cls in classes:
                 c = classes[cls]
-                roof.setdefault("other_tensor_kernels", []).append(
+                roof.setdefault("serial_pass_tensor_kernels", []).append(
                     {"kernel": c["kernel"], "achieved_tflops": c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e12,
                      "ms_per_step": c["ms_per_step"], "launches_per_step": c["launches_per_step"],
-                     "share_of_step": c["share_of_serial_step"]})
+                     "share_of_serial_step": c["share_of_serial_step"]})
     for cls, key in ((1, "attention"), (2, "layernorm")):
         if cls in classes:
             c = classes[cls]
             gbs = c["work_per_step"] / (c["ms_per_step"] * 1e-3) / 1e9
             hbm[key] = {"achieved_gbs": gbs, "frac": gbs / pk["hbm_gbs"], "ms_per_step": c["ms_per_step"],
-                        "launches_per_step": c["launches_per_step"], "share_of_step": c["share_of_serial_step"]}
+                        "launches_per_step": c["launches_per_step"], "share_of_serial_step": c["share_of_serial_step"]}
 
     # ---------------- data-parallel correctness on this hardware (N > 1, outside every timed region) ----------------
     dp_check = None

@@ -148,6 +148,12 @@ FV_API int fervit_debug_gemm_clock(double* ns, double* cycles) {
   return gemm_tc2_clock_probe(ns, cycles);
 }
 
+FV_API int fervit_gemm_prof(int op, void* stream) { return gemm_tc2_prof(op, S_(stream)); }
+FV_API int fervit_gemm_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap) {
+  FV_CHECK(us && flops && launches, "gemm_prof_read: null argument");
+  return gemm_tc2_prof_read(us, flops, launches, per_launch, cap);
+}
+
 FV_API int fervit_debug_gemm_timeline(unsigned long long* out, int n) {
   FV_CHECK(out, "debug_gemm_timeline: null argument");
   return gemm_tc2_timeline(out, n);

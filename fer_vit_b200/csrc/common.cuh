@@ -168,6 +168,83 @@ __device__ __forceinline__ void gelu_fwd_deriv_poly(float u, float& g, float& d)
   g = u * cdf;
   d = fmaf(u * 0.39894228040143267794f, e, cdf);
 }
+// Two elements per instruction: Blackwell's packed fp32 pipe (fma/mul.rn.f32x2 -> FFMA2 / FMUL2, same IEEE fp32 results
+// as the scalar forms above). The GELU GEMM epilogues are bound by warp-instruction ISSUE, not by fp32 throughput
+// (profiles/r02_gemm_timeline.jsonl: 6.2 us of epilogue per 128 x 256 tile against 4.2-4.8 us of MMAs); packing halves
+// the issue slots of the polynomial: 9.5 instead of 19 per element. The clamp of u is replaced by ONE min on u^2 and a
+// saturating final FMA: for |u| > 4, u * P8(16) overshoots +-0.5, and .sat clamps the cdf to [0, 1] (exact there to
+// 3.2e-5, as before).
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+#define FV_F2C(v) f2_pack((v), (v))
+// cdf Phi(u) of two elements; s = u^2 (both) is returned for the density
+__device__ __forceinline__ void gelu_cdf2(float u0, float u1, unsigned long long u, unsigned long long& s, float& c0,
+                                          float& c1) {
+  s = f2_mul(u, u);
+  float s0, s1;
+  f2_unpack(s, s0, s1);
+  const unsigned long long sc = f2_pack(fminf(s0, 16.0f), fminf(s1, 16.0f));
+  unsigned long long p = FV_F2C(3.463219783e-01f / 4294967296.0f);
+  p = f2_fma(p, sc, FV_F2C(-1.879982349e+00f / 268435456.0f));
+  p = f2_fma(p, sc, FV_F2C(4.556960448e+00f / 16777216.0f));
+  p = f2_fma(p, sc, FV_F2C(-6.600791621e+00f / 1048576.0f));
+  p = f2_fma(p, sc, FV_F2C(6.482043223e+00f / 65536.0f));
+  p = f2_fma(p, sc, FV_F2C(-4.644546053e+00f / 4096.0f));
+  p = f2_fma(p, sc, FV_F2C(2.528634271e+00f / 256.0f));
+  p = f2_fma(p, sc, FV_F2C(-1.062569537e+00f / 16.0f));
+  p = f2_fma(p, sc, FV_F2C(3.989227100e-01f));
+  float p0, p1;
+  f2_unpack(p, p0, p1);
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(c0) : "f"(u0), "f"(p0));
+  asm("fma.rn.sat.f32 %0, %1, %2, 0f3F000000;" : "=f"(c1) : "f"(u1), "f"(p1));
+}
+// (x0, x1) <- GELU(x0, x1)
+__device__ __forceinline__ void gelu_fwd_poly2(float& x0, float& x1) {
+  const unsigned long long u = f2_pack(x0, x1);
+  unsigned long long s;
+  float c0, c1;
+  gelu_cdf2(x0, x1, u, s, c0, c1);
+  f2_unpack(f2_mul(u, f2_pack(c0, c1)), x0, x1);
+}
+// (x0, x1) <- GELU(x0, x1), (d0, d1) <- GELU'(x0, x1)
+__device__ __forceinline__ void gelu_fwd_deriv_poly2(float& x0, float& x1, float& d0, float& d1) {
+  const unsigned long long u = f2_pack(x0, x1);
+  unsigned long long s;
+  float c0, c1;
+  gelu_cdf2(x0, x1, u, s, c0, c1);
+  float t0, t1, e0, e1;
+  f2_unpack(f2_mul(s, FV_F2C(-0.5f * 1.44269504088896340736f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));   // exp(-u^2 / 2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  const unsigned long long cdf = f2_pack(c0, c1);
+  const unsigned long long g = f2_mul(u, cdf);
+  const unsigned long long d = f2_fma(f2_mul(u, FV_F2C(0.39894228040143267794f)), f2_pack(e0, e1), cdf);
+  f2_unpack(g, x0, x1);
+  f2_unpack(d, d0, d1);
+}
+#endif
 __host__ __device__ __forceinline__ float gelu_bwd_poly(float u) {
   const float uc = fminf(fmaxf(u, -4.0f), 4.0f);
   const float s = uc * uc;

@@ -32,6 +32,7 @@
 #include "tc_ptx.cuh"
 #include "gemm_tc2_sched.cuh"
 #include <stdlib.h>
+#include <vector>
 
 namespace fervit {
 namespace tc2 {
@@ -172,6 +173,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   // everything above is independent of the previous kernel's output (PDL): wait for it only now
   pdl_grid_sync();
   if (threadIdx.x == 0) TL(TL_GRIDSYNC);
+  if (p.prof && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMin(p.prof, t);
+  }
 
   if (warp == W_TMA) {
     // ===================== TMA producer (both CTAs) =====================
@@ -516,7 +522,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float4 bb = __ldg(b4 + i);
-              v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
+              f2_unpack(f2_add(f2_pack(v[4 * i], v[4 * i + 1]), f2_pack(bb.x, bb.y)), v[4 * i], v[4 * i + 1]);
+              f2_unpack(f2_add(f2_pack(v[4 * i + 2], v[4 * i + 3]), f2_pack(bb.z, bb.w)), v[4 * i + 2], v[4 * i + 3]);
             }
           }
           if (C::BWD_ACT) {
@@ -529,8 +536,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               for (int t = 0; t < 4; ++t) {
                 const float2 f = unpack_bf16x2(aw[t]);
                 if (KIND == EPK_MUL_BWD) {   // the forward pass saved act'(pre)
-                  v[8 * c + 2 * t] *= f.x;
-                  v[8 * c + 2 * t + 1] *= f.y;
+                  f2_unpack(f2_mul(f2_pack(v[8 * c + 2 * t], v[8 * c + 2 * t + 1]), f2_pack(f.x, f.y)), v[8 * c + 2 * t],
+                            v[8 * c + 2 * t + 1]);
                 } else if (KIND == EPK_GELU_BWD) {
                   v[8 * c + 2 * t] *= gelu_bwd_poly(f.x);
                   v[8 * c + 2 * t + 1] *= gelu_bwd_poly(f.y);
@@ -557,15 +564,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               for (int c = 0; c < 8; ++c) {
                 float d[8];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                  float& x = v[8 * c + t];
+                for (int t = 0; t < 8; t += 2) {
+                  float& x0 = v[8 * c + t];
+                  float& x1 = v[8 * c + t + 1];
                   if (KIND == EPK_GELU) {
-                    float gg;
-                    gelu_fwd_deriv_poly(x, gg, d[t]);
-                    x = gg;
+                    gelu_fwd_deriv_poly2(x0, x1, d[t], d[t + 1]);   // FFMA2: two elements per instruction
                   } else {
-                    d[t] = x > 0.0f ? 1.0f : 0.0f;
-                    x = fmaxf(x, 0.0f);
+                    d[t] = x0 > 0.0f ? 1.0f : 0.0f;
+                    d[t + 1] = x1 > 0.0f ? 1.0f : 0.0f;
+                    x0 = fmaxf(x0, 0.0f);
+                    x1 = fmaxf(x1, 0.0f);
                   }
                 }
                 *reinterpret_cast<uint4*>(zrow + ((c ^ sw) << 4)) =
@@ -581,7 +589,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
                                  pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), pack_bf16x2(v[8 * c + 6], v[8 * c + 7]));
               }
 #pragma unroll
-              for (int i = 0; i < 64; ++i) v[i] = (KIND == EPK_GELU) ? gelu_fwd_poly(v[i]) : fmaxf(v[i], 0.0f);
+              for (int i = 0; i < 64; i += 2) {
+                if (KIND == EPK_GELU) {
+                  gelu_fwd_poly2(v[i], v[i + 1]);
+                } else {
+                  v[i] = fmaxf(v[i], 0.0f);
+                  v[i + 1] = fmaxf(v[i + 1], 0.0f);
+                }
+              }
             }
           }
           if (p.has_out) {
@@ -616,6 +631,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   cluster_sync();
   tc_fence_after();
   if (threadIdx.x == 0) TL(TL_FINAL_SYNC);
+  if (p.prof && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(p.prof + 1, t);
+  }
   if (warp == W_ALLOC) tmem_dealloc<2>(tmem_base, (uint32_t)C::TMEM_COLS);
   if (tl_row >= 0 && threadIdx.x == 0) {
     TL(TL_END);
@@ -680,6 +700,16 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, u
 namespace tc2 {
 
 constexpr int SK_FLAG_BYTES = 4096;
+
+// In-kernel launch timer: while switched on, every launch takes the next slot of g_prof_ts and its CTAs record
+// {first start after the grid dependency, last exit} in %globaltimer nanoseconds. A graph captured while it is on keeps
+// its slots, so the launches of one REPLAY can be timed where they run (PDL edges and parallel branches intact).
+constexpr int PROF_SLOTS = 4096;
+__device__ unsigned long long g_prof_ts[PROF_SLOTS][2];
+static bool g_prof_on = false;
+static int g_prof_next = 0;
+static double g_prof_flops[PROF_SLOTS];
+static int g_prof_shape[PROF_SLOTS][4];   // M, N, K, epilogue kind (+ 16 * F32 variant)
 // process-wide default scratch (fervit_set_gemm_scratch) for callers of the stand-alone GEMM entry points; the plan
 // passes its own region through the Epilogue
 static void* g_sk_ws = nullptr;
@@ -762,6 +792,15 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
     const int sk_pairs = (int)(((long long)p.sk_tiles * ceil_div(K, BK) + p.sk_q - 1) / p.sk_q);
     if (sk_pairs > pairs) pairs = sk_pairs;
   }
+  p.prof = nullptr;
+  if (g_prof_on && g_prof_next < PROF_SLOTS) {
+    static unsigned long long* base = nullptr;
+    if (!base) FV_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_prof_ts));
+    g_prof_flops[g_prof_next] = 2.0 * M * (double)N * K;
+    g_prof_shape[g_prof_next][0] = M; g_prof_shape[g_prof_next][1] = N; g_prof_shape[g_prof_next][2] = K;
+    g_prof_shape[g_prof_next][3] = KIND + 16 * F32;
+    p.prof = base + 2 * (size_t)g_prof_next++;
+  }
   ProfScope prof(0, 2.0 * M * (double)N * K, stream);
   FV_CUDA(launch_pdl(kernel, dim3(2 * pairs), dim3(THREADS), (size_t)C::SMEM_BYTES, stream, ta, tb, ty, tz, tx, tr, p));
   FV_COUNT_LAUNCH();
@@ -789,6 +828,48 @@ int gemm_tc2_clock_probe(double* ns, double* cycles) {
   FV_CUDA(cudaMemcpyFromSymbol(h, tc2::g_clock_probe, sizeof(h)));
   *ns = (double)(h[1] - h[0]);
   *cycles = (double)(h[3] - h[2]);
+  return 0;
+}
+
+// In-kernel launch timer of the CTA-pair GEMM. op 1: switch on and restart slot numbering; op 2: clear the recorded
+// stamps of the slots handed out so far (asynchronously on `stream`: enqueue it before the replay to be timed);
+// op 0: switch off (graphs captured meanwhile keep stamping their slots).
+int gemm_tc2_prof(int op, cudaStream_t stream) {
+  if (op == 1) { tc2::g_prof_on = true; tc2::g_prof_next = 0; return 0; }
+  if (op == 0) { tc2::g_prof_on = false; return 0; }
+  FV_CHECK(op == 2, "gemm prof: unknown op %d", op);
+  if (tc2::g_prof_next == 0) return 0;
+  static std::vector<unsigned long long> init;
+  if ((int)init.size() < 2 * tc2::g_prof_next) {
+    init.resize(2 * tc2::PROF_SLOTS);
+    for (int i = 0; i < tc2::PROF_SLOTS; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+  }
+  void* base = nullptr;
+  FV_CUDA(cudaGetSymbolAddress(&base, tc2::g_prof_ts));
+  FV_CUDA(cudaMemcpyAsync(base, init.data(), sizeof(unsigned long long) * 2 * tc2::g_prof_next, cudaMemcpyHostToDevice,
+                          stream));
+  return 0;
+}
+// Sum over the slots (blocking copy): device microseconds, FLOPs, launches; optionally one record per launch
+// ({us, flops, M, N, K, kind}, `cap` records of 6 doubles).
+int gemm_tc2_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap) {
+  const int n = tc2::g_prof_next;
+  std::vector<unsigned long long> h(2 * (size_t)(n > 0 ? n : 1));
+  if (n > 0) FV_CUDA(cudaMemcpyFromSymbol(h.data(), tc2::g_prof_ts, sizeof(unsigned long long) * 2 * n));
+  double t = 0, f = 0;
+  long long cnt = 0;
+  for (int i = 0; i < n; ++i) {
+    if (h[2 * i] == ~0ull || h[2 * i + 1] < h[2 * i]) continue;   // slot not run since the last reset
+    const double d = (double)(h[2 * i + 1] - h[2 * i]) * 1e-3;
+    t += d; f += tc2::g_prof_flops[i];
+    if (per_launch && cnt < cap) {
+      double* r = per_launch + 6 * cnt;
+      r[0] = d; r[1] = tc2::g_prof_flops[i];
+      for (int k = 0; k < 4; ++k) r[2 + k] = tc2::g_prof_shape[i][k];
+    }
+    ++cnt;
+  }
+  *us = t; *flops = f; *launches = cnt;
   return 0;
 }
 

@@ -39,6 +39,9 @@ struct Params {
   float* sk_ws;   // [pairs][2][BM][BN] fp32
   int* sk_flags;  // [sk_tiles][2] arrival counters, zero between launches
   int debug;  // timing experiments only (results are garbage): 1 no TMA loads, 2 no MMAs, 4 no epilogue, 8 record clocks
+  // in-kernel launch timer (fervit_gemm_prof): {min over CTAs of %globaltimer once the grid dependency has resolved,
+  // max over CTAs at exit}; null = off. Works inside CUDA-graph replays, where host-side events cannot sit.
+  unsigned long long* prof;
 };
 
 

@@ -344,6 +344,16 @@ int fervit_set_gemm_scratch(void* ptr, long long bytes);
  * cycle count (clock64) of its CTA 0; cycles / ns = the SM clock in GHz while the kernel ran. */
 int fervit_debug_gemm_clock(double* ns, double* cycles);
 
+/* In-kernel launch timer of the CTA-pair tcgen05 GEMM (bench.py's roofline leg). While on, every launch takes the next
+ * slot and its CTAs record {first start once the grid dependency has resolved, last exit} in %globaltimer ns; a CUDA
+ * graph captured while it is on keeps its slots, so the launches of one replay are timed where they run (PDL edges and
+ * parallel branches intact — host-side events cannot sit there). op 1: on, restart slot numbering; op 2: clear the
+ * stamps recorded so far (async on `stream`, enqueue before the replay to be timed); op 0: off.
+ * read: sum over the slots stamped since the last clear — device microseconds, FLOPs (2MNK), launches; per_launch
+ * (optional, cap records of 6 doubles): {us, flops, M, N, K, epilogue kind + 16 * fp32 variant}. */
+int fervit_gemm_prof(int op, void* stream);
+int fervit_gemm_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap);
+
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 64 set, the CTA-pair GEMM stamps clock64 at every phase boundary of two CTAs
  * (row 0: CTA 0, row 1: leader of the last pair); out receives 2 x 32 values (slot meanings: csrc/gemm_tc2.cu TL_*). */
 int fervit_debug_gemm_timeline(unsigned long long* out, int n);

@@ -185,16 +185,18 @@ def test_per_parameter_requires_grad_inside_blocks(precision):
     for k in frozen:
         named[k].requires_grad_(False)
     model.zero_grad(set_to_none=True)
-    loss = fv.cross_entropy(model(g["x"].cuda()), g["y"].cuda())
+    w = g["class_weight"].cuda() if g["class_weight"] is not None else None
+    loss = fv.cross_entropy(model(g["x"].cuda()), g["y"].cuda(), w, g["label_smoothing"])
     loss.backward()
     torch.cuda.synchronize()
     tol = 1e-4 if precision == "fp32" else 2e-2
-    worst = 0.0
+    errs = {}
     for k, p in named.items():
         if k in frozen:
             assert p.grad is None, k
         else:
             assert p.grad is not None, k
-            worst = max(worst, relerr(p.grad, g["grad"][k]))
-    record("per_parameter_requires_grad", precision=precision, worst_grad=worst)
-    assert worst < tol, worst
+            errs[k] = relerr(p.grad, g["grad"][k])
+    worst = max(errs, key=errs.get)
+    record("per_parameter_requires_grad", precision=precision, worst_grad=errs[worst], worst_key=worst)
+    assert errs[worst] < tol, (worst, errs[worst])

@@ -10,6 +10,7 @@
 //   mode 1  cluster 2: the two CTAs need the SAME A box; each loads half of it (64 rows) and multicasts to both
 //   mode 2  cluster 4: four CTAs share the A box (32 rows each, multicast to all four)
 //   mode 3  cluster 2: the two CTAs need the same A box and both load all of it (unicast duplicates)
+//   mode 5  cluster 1, B only (A skipped): 16 KB per k-block
 //   mode 4  cluster 1: A only (16 KB per k-block)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -70,44 +71,43 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
+  const int total = a.tiles * a.kblocks;
   if (threadIdx.x == 0) {
+    // ---- producer (one lane, like the GEMM's TMA warp) ----
     const int group = blockIdx.x / cs;              // CTAs of one cluster share the A rows of `group`
     const int ngroups = gridDim.x / cs;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    const long long c0 = clock64();
-    const int total = a.tiles * a.kblocks;
     const bool with_b = a.mode != 4;
     const uint32_t bytes = BOX_BYTES + (with_b ? BOX_BYTES : 0);
     const int sub = BOX_ROWS / cs;                  // rows of the shared A box this CTA fetches (multicast modes)
-    for (int i = 0; i < total + STAGES - 1; ++i) {
-      if (i < total) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        if (i >= STAGES) wait(&empty[s], ph ^ 1, 1);
-        const int tile = i / a.kblocks, kb = i % a.kblocks;
-        const int unit = group + tile * ngroups;                 // like the GEMM: n fastest
-        const int mb = (unit / a.n_blocks) % a.m_blocks, nb = unit % a.n_blocks;
-        expect_tx(&full[s], bytes);
-        uint8_t* sa = smem + s * 2 * BOX_BYTES;
-        uint8_t* sb = sa + BOX_BYTES;
-        if (a.mode == 1 || a.mode == 2) {
-          tma_load_mc(sa + rank * sub * 128, &tm_as, &full[s], kb * BOX_COLS, mb * BOX_ROWS + (int)rank * sub,
-                      (uint16_t)((1u << cs) - 1));
-        } else if (a.mode == 3) {
-          tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, mb * BOX_ROWS);
-        } else {
-          tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, (blockIdx.x % a.m_blocks) * BOX_ROWS + 0 * mb);
-        }
-        if (with_b) tma_load(sb, &tm_b, &full[s], kb * BOX_COLS, ((nb * cs + (int)rank) % (a.n_blocks * 2)) * BOX_ROWS);
+    for (int i = 0; i < total; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (i / STAGES) & 1;
+      if (i >= STAGES) wait(&empty[s], ph ^ 1, 1);
+      const int tile = i / a.kblocks, kb = i % a.kblocks;
+      const int unit = group + tile * ngroups;                 // like the GEMM: n fastest
+      const int mb = (unit / a.n_blocks) % a.m_blocks, nb = unit % a.n_blocks;
+      expect_tx(&full[s], bytes);
+      uint8_t* sa = smem + s * 2 * BOX_BYTES;
+      uint8_t* sb = sa + BOX_BYTES;
+      if (a.mode == 1 || a.mode == 2) {
+        tma_load_mc(sa + rank * sub * 128, &tm_as, &full[s], kb * BOX_COLS, mb * BOX_ROWS + (int)rank * sub,
+                    (uint16_t)((1u << cs) - 1));
+      } else {
+        tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, mb * BOX_ROWS);
       }
-      const int j = i - (STAGES - 1);
-      if (j >= 0) {
-        const int sj = j % STAGES;
-        wait(&full[sj], (j / STAGES) & 1, 2);
-        if (cs == 1) arrive_remote(mapa(smem_u32(&empty[sj]), 0));
-        else for (int r = 0; r < cs; ++r) arrive_remote(mapa(smem_u32(&empty[sj]), r));
-      }
+      if (with_b) tma_load(sb, &tm_b, &full[s], kb * BOX_COLS, ((nb * cs + (int)rank) % (a.n_blocks * 2)) * BOX_ROWS);
+    }
+  } else if (threadIdx.x == 32) {
+    // ---- consumer (one lane, like the GEMM's MMA warp): drop the stage as soon as it has landed ----
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const long long c0 = clock64();
+    uint32_t eaddr[4];
+    for (int r = 0; r < cs; ++r) eaddr[r] = 0;
+    for (int j = 0; j < total; ++j) {
+      const int sj = j % STAGES;
+      wait(&full[sj], (j / STAGES) & 1, 2);
+      for (int r = 0; r < cs; ++r) arrive_remote(mapa(smem_u32(&empty[sj]), r));
     }
     const long long c1 = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -161,7 +161,7 @@ int main() {
       if (cs == 4) grid = 144;
       CUtensorMap ta = make_map(fn, A, M, K, BOX_ROWS), tas = make_map(fn, A, M, K, BOX_ROWS / cs),
                   tb = make_map(fn, B, N, K, BOX_ROWS);
-      Args a{mode, cs, 8, K / BOX_COLS, M / BOX_ROWS, N / 256, out};
+      Args a{mode, cs, 16, K / BOX_COLS, M / BOX_ROWS, N / 256, out};
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(grid); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
       cudaLaunchAttribute at[1];
@@ -179,7 +179,7 @@ int main() {
       CK(cudaMemcpy(h, out, grid * 16, cudaMemcpyDeviceToHost));
       double ns = 0, cyc = 0;
       for (int i = 0; i < grid; ++i) { if (h[2 * i] > ns) ns = (double)h[2 * i]; if (h[2 * i + 1] > cyc) cyc = (double)h[2 * i + 1]; }
-      const double per_cta = 8.0 * (K / BOX_COLS) * (mode == 4 ? 1 : 2) * BOX_BYTES;
+      const double per_cta = 16.0 * (K / BOX_COLS) * (mode == 4 ? 1 : 2) * BOX_BYTES;
       if (rep == 1)
         printf("{\"mode\": %d, \"cluster\": %d, \"grid\": %d, \"kernel_us\": %.2f, \"event_us\": %.2f, \"ingest_bytes_per_cta\": %.0f, "
                "\"ingest_B_per_clk_per_sm\": %.1f, \"ingest_TBps_chip\": %.2f, \"sm_ghz\": %.3f}\n",
