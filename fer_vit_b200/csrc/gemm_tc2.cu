@@ -91,11 +91,14 @@ struct Cfg {
 // [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
 __device__ unsigned long long g_clock_probe[4];
 // debug bit 64: clock64 stamps of the phases of two CTAs (row 0: CTA 0, row 1: leader of the last pair); slots in TL_*
-constexpr int TL_N = 32;
+constexpr int TL_N = 64;
 __device__ unsigned long long g_timeline[2][TL_N];
 enum { TL_ENTRY = 0, TL_PROLOGUE = 1, TL_GRIDSYNC = 2, TL_FIRST_FULL = 3, TL_MMA_ISSUED = 4 /* +it, it < 4 */,
        TL_TMA_FIRST = 8, TL_TMA_LAST = 9, TL_ACC_READY = 10 /* +2*it */, TL_EPI_DONE = 11 /* +2*it */,
-       TL_STORES_READ = 18, TL_FINAL_SYNC = 19, TL_END = 20, TL_EPI7_DONE = 21 /* +it */, TL_GT0 = 30, TL_GT1 = 31 };
+       TL_STORES_READ = 18, TL_FINAL_SYNC = 19, TL_END = 20, TL_EPI7_DONE = 21 /* +it */, TL_GT0 = 30, TL_GT1 = 31,
+       // item 0, warp 0, chunk j < 4: 32 + 6*j + {0 side input landed, 1 accumulator in registers, 2 math done,
+       // 3 staging tile free (earlier stores have read it), 4 staged + fenced, 5 stores issued}
+       TL_CHUNK = 32 };
 
 template <int BN, int KIND, int F32, bool SK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
@@ -376,8 +379,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int j = 0; j < nch; ++j, ++g) {
           const uint32_t b = g % XB, yb = g & 1;
           const int col = col0 + j * CW;
+          const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4);
           if (res) mbar_wait(&my_ld[b], (g / XB) & 1, 5);
+          if (tlc) TL(TL_CHUNK + 6 * j + 0);
           tmem_ld_wait();
+          if (tlc) TL(TL_CHUNK + 6 * j + 1);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -418,8 +424,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             for (int i = 0; i < 32; ++i) v[i] *= alpha;
           }
           // the bf16 tile [yb] was last the source of chunk g-2's stores (and, without a residual, the fp32 tile too)
+          if (tlc) TL(TL_CHUNK + 6 * j + 2);
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
+          if (tlc) TL(TL_CHUNK + 6 * j + 3);
           uint8_t* xrow = Xs + b * XT + r * 128;
           if (res) {
 #pragma unroll
@@ -444,6 +452,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (tlc) TL(TL_CHUNK + 6 * j + 4);
           if (lane == 0) {
             if (p.has_out) tma_store_2d(&tm_y, Ys + yb * YT, col, row0);
             if (p.has_f32) tma_store_2d(&tm_x, Xs + b * XT, col, row0);
@@ -453,6 +462,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               issue_load(g + XB, col + (int)XB * CW);
             }
           }
+          if (tlc) TL(TL_CHUNK + 6 * j + 5);
         }
       } else {
         // ------------------------------------------------------------------------------------------------
@@ -485,8 +495,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           uint32_t ra[32], rb[32];
           tmem_ld32(taddr0 + (uint32_t)(j * CW), ra);
           tmem_ld32(taddr0 + (uint32_t)(j * CW + 32), rb);
+          const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4);
           if (C::BWD_ACT) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
+          if (tlc) TL(TL_CHUNK + 6 * j + 0);
           tmem_ld_wait();
+          if (tlc) TL(TL_CHUNK + 6 * j + 1);
           if (j == nch - 1) {
             // last read of this accumulator buffer: hand it back to the MMA issuer before doing the math
             tc_fence_before();
@@ -554,8 +567,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           // the single-buffered output tiles were the source of the previous chunk's stores, issued a whole chunk
           // of TMEM loads and math ago
+          if (tlc) TL(TL_CHUNK + 6 * j + 2);
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
+          if (tlc) TL(TL_CHUNK + 6 * j + 3);
           if (C::FWD_ACT) {
             uint8_t* zrow = Zs + r * 128;
             if (p.has_z && p.pre_is_deriv) {
@@ -609,12 +624,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
+          if (tlc) TL(TL_CHUNK + 6 * j + 4);
           if (lane == 0) {
             if (p.has_out) tma_store_2d(&tm_y, Ys, col, row0);
             if (C::FWD_ACT && p.has_z) tma_store_2d(&tm_z, Zs, col, row0);
             tma_store_commit();
             if (C::BWD_ACT && j + 2 < nch) issue_aux(g + 2, col + 2 * CW);  // tile [b] was consumed above
           }
+          if (tlc) TL(TL_CHUNK + 6 * j + 5);
         }
       }
       if (lane == 0 && it < 4) {
@@ -876,6 +893,8 @@ int gemm_tc2_prof_read(double* us, double* flops, long long* launches, double* p
 // diagnostics (FERVIT_GEMM_DEBUG bit 64): phase stamps of two CTAs of the last CTA-pair GEMM, 2 x 32 values
 int gemm_tc2_timeline(unsigned long long* out, int n) {
   FV_CHECK(n >= 2 * tc2::TL_N, "gemm timeline: need room for %d values", 2 * tc2::TL_N);
+  static bool cleared = false;
+  (void)cleared;
   FV_CUDA(cudaMemcpyFromSymbol(out, tc2::g_timeline, sizeof(unsigned long long) * 2 * tc2::TL_N));
   return 0;
 }

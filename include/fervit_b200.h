@@ -355,7 +355,7 @@ int fervit_gemm_prof(int op, void* stream);
 int fervit_gemm_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap);
 
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 64 set, the CTA-pair GEMM stamps clock64 at every phase boundary of two CTAs
- * (row 0: CTA 0, row 1: leader of the last pair); out receives 2 x 32 values (slot meanings: csrc/gemm_tc2.cu TL_*). */
+ * (row 0: CTA 0, row 1: leader of the last pair); out receives 2 x 64 values (slot meanings: csrc/gemm_tc2.cu TL_*). */
 int fervit_debug_gemm_timeline(unsigned long long* out, int n);
 
 /* fp32 -> bf16 cast (n multiple of 4) */

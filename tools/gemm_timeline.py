@@ -22,6 +22,11 @@ from fer_vit_b200 import _lib as L  # noqa: E402
 
 SLOTS = {0: "entry", 1: "prologue done", 2: "grid dependency", 3: "first operands landed", 8: "first TMA issued",
          9: "last TMA issued", 18: "stores drained", 19: "final cluster sync", 20: "end"}
+CHUNK = ["side input landed", "accumulator in registers", "math done", "staging tile free", "staged + fenced",
+         "stores issued"]
+for j in range(4):
+    for k, nm in enumerate(CHUNK):
+        SLOTS[32 + 6 * j + k] = f"item 0 chunk {j}: {nm}"
 for it in range(4):
     SLOTS[4 + it] = f"MMAs of item {it} issued"
     SLOTS[10 + 2 * it] = f"accumulator {it} ready (warp 0)"
@@ -69,11 +74,11 @@ def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd
         e0.record(); launch(); e1.record()
         torch.cuda.synchronize()
         ev.append(e0.elapsed_time(e1) * 1e3)
-    buf = (ctypes.c_ulonglong * 64)()
-    L.check(lib.fervit_debug_gemm_timeline(buf, 64))
+    buf = (ctypes.c_ulonglong * 128)()
+    L.check(lib.fervit_debug_gemm_timeline(buf, 128))
     rows = []
     for row in range(2):
-        t = list(buf[row * 32:(row + 1) * 32])
+        t = list(buf[row * 64:(row + 1) * 64])
         cyc = t[20] - t[0]
         ns = t[31] - t[30]
         ghz = cyc / max(ns, 1)

@@ -10,7 +10,7 @@
 //   mode 1  cluster 2: the two CTAs need the SAME A box; each loads half of it (64 rows) and multicasts to both
 //   mode 2  cluster 4: four CTAs share the A box (32 rows each, multicast to all four)
 //   mode 3  cluster 2: the two CTAs need the same A box and both load all of it (unicast duplicates)
-//   mode 5  cluster 1, B only (A skipped): 16 KB per k-block
+//   mode 6  cluster 1, two producer lanes (one issues the A boxes, one the B boxes)
 //   mode 4  cluster 1: A only (16 KB per k-block)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -63,7 +63,7 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   const uint32_t rank = a.cluster > 1 ? ctarank() : 0;
   const int cs = a.cluster;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], cs); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], a.mode == 6 ? 2 : 1); mbar_init(&empty[s], cs); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -72,30 +72,34 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
   const int total = a.tiles * a.kblocks;
-  if (threadIdx.x == 0) {
-    // ---- producer (one lane, like the GEMM's TMA warp) ----
+  if (threadIdx.x == 0 || (a.mode == 6 && threadIdx.x == 64)) {
+    // ---- producer (one lane, like the GEMM's TMA warp; mode 6: a second lane issues the B boxes) ----
     const int group = blockIdx.x / cs;              // CTAs of one cluster share the A rows of `group`
     const int ngroups = gridDim.x / cs;
-    const bool with_b = a.mode != 4;
-    const uint32_t bytes = BOX_BYTES + (with_b ? BOX_BYTES : 0);
+    const bool two = a.mode == 6;
+    const bool do_a = !two || threadIdx.x == 0, do_b = a.mode != 4 && (!two || threadIdx.x == 64);
+    const uint32_t bytes = (do_a ? BOX_BYTES : 0) + (do_b ? BOX_BYTES : 0);
     const int sub = BOX_ROWS / cs;                  // rows of the shared A box this CTA fetches (multicast modes)
-    for (int i = 0; i < total; ++i) {
-      const int s = i % STAGES;
-      const uint32_t ph = (i / STAGES) & 1;
-      if (i >= STAGES) wait(&empty[s], ph ^ 1, 1);
-      const int tile = i / a.kblocks, kb = i % a.kblocks;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = 0; tile < a.tiles; ++tile) {
       const int unit = group + tile * ngroups;                 // like the GEMM: n fastest
       const int mb = (unit / a.n_blocks) % a.m_blocks, nb = unit % a.n_blocks;
-      expect_tx(&full[s], bytes);
-      uint8_t* sa = smem + s * 2 * BOX_BYTES;
-      uint8_t* sb = sa + BOX_BYTES;
-      if (a.mode == 1 || a.mode == 2) {
-        tma_load_mc(sa + rank * sub * 128, &tm_as, &full[s], kb * BOX_COLS, mb * BOX_ROWS + (int)rank * sub,
-                    (uint16_t)((1u << cs) - 1));
-      } else {
-        tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, mb * BOX_ROWS);
+      const int row_a = mb * BOX_ROWS + ((a.mode == 1 || a.mode == 2) ? (int)rank * sub : 0);
+      const int row_b = ((nb * cs + (int)rank) % (a.n_blocks * 2)) * BOX_ROWS;
+      for (int kb = 0; kb < a.kblocks; ++kb) {
+        if (tile > 0 || kb >= STAGES) wait(&empty[s], ph ^ 1, 1);
+        expect_tx(&full[s], bytes);
+        uint8_t* sa = smem + s * 2 * BOX_BYTES;
+        if (do_a) {
+          if (a.mode == 1 || a.mode == 2)
+            tma_load_mc(sa + rank * sub * 128, &tm_as, &full[s], kb * BOX_COLS, row_a, (uint16_t)((1u << cs) - 1));
+          else
+            tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, row_a);
+        }
+        if (do_b) tma_load(sa + BOX_BYTES, &tm_b, &full[s], kb * BOX_COLS, row_b);
+        if (++s == STAGES) { s = 0; ph ^= 1; }
       }
-      if (with_b) tma_load(sb, &tm_b, &full[s], kb * BOX_COLS, ((nb * cs + (int)rank) % (a.n_blocks * 2)) * BOX_ROWS);
     }
   } else if (threadIdx.x == 32) {
     // ---- consumer (one lane, like the GEMM's MMA warp): drop the stage as soon as it has landed ----
@@ -153,9 +157,9 @@ int main() {
   const int smem = STAGES * 2 * BOX_BYTES + 1024 + 256;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  const int modes[5][2] = {{0, 1}, {1, 2}, {2, 4}, {3, 2}, {4, 1}};
+  const int modes[6][2] = {{0, 1}, {1, 2}, {2, 4}, {3, 2}, {4, 1}, {6, 1}};
   for (int rep = 0; rep < 2; ++rep)
-    for (int mi = 0; mi < 5; ++mi) {
+    for (int mi = 0; mi < 6; ++mi) {
       const int mode = modes[mi][0], cs = modes[mi][1];
       int grid = 148 / cs * cs;
       if (cs == 4) grid = 144;
