@@ -431,9 +431,10 @@ def main():
     blocker = int(0.045 * 1.9e9)   # ~45 ms of spin: one host-launched step takes the host ~5-8 ms to enqueue
 
     def serial_pass(mode):
-        lib.fervit_profile_enable(mode)
-        eager_step(pool_x[0], pool_y[0])
+        lib.fervit_profile_enable(2)
+        eager_step(pool_x[0], pool_y[0])      # untimed: allocator, caches
         torch.cuda.synchronize()
+        lib.fervit_profile_enable(mode)       # mode 1 clears the records and starts recording
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda._sleep(blocker)
         e0.record()

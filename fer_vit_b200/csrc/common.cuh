@@ -168,6 +168,25 @@ __device__ __forceinline__ void gelu_fwd_deriv_poly(float u, float& g, float& d)
   g = u * cdf;
   d = fmaf(u * 0.39894228040143267794f, e, cdf);
 }
+// Scalar mirror of the packed (f32x2) epilogue math below, op for op (same fmaf order, same saturating final FMA): the
+// host-side test (tests/host/mix_hash_host.cu) checks it against erf, the kernels use the packed form.
+__host__ __device__ __forceinline__ void gelu_fwd_deriv_packed_mirror(float u, float& g, float& d) {
+  const float s = u * u;
+  const float sc = fminf(s, 16.0f);
+  float p = 3.463219783e-01f / 4294967296.0f;
+  p = fmaf(p, sc, -1.879982349e+00f / 268435456.0f);
+  p = fmaf(p, sc, 4.556960448e+00f / 16777216.0f);
+  p = fmaf(p, sc, -6.600791621e+00f / 1048576.0f);
+  p = fmaf(p, sc, 6.482043223e+00f / 65536.0f);
+  p = fmaf(p, sc, -4.644546053e+00f / 4096.0f);
+  p = fmaf(p, sc, 2.528634271e+00f / 256.0f);
+  p = fmaf(p, sc, -1.062569537e+00f / 16.0f);
+  p = fmaf(p, sc, 3.989227100e-01f);
+  const float cdf = fminf(fmaxf(fmaf(u, p, 0.5f), 0.0f), 1.0f);   // fma.rn.sat: |u| > 4 overshoots and clamps
+  const float e = exp2f(s * (-0.5f * 1.44269504088896340736f));   // device: ex2.approx
+  g = u * cdf;
+  d = fmaf(u * 0.39894228040143267794f, e, cdf);
+}
 // Two elements per instruction: Blackwell's packed fp32 pipe (fma/mul.rn.f32x2 -> FFMA2 / FMUL2, same IEEE fp32 results
 // as the scalar forms above). The GELU GEMM epilogues are bound by warp-instruction ISSUE, not by fp32 throughput
 // (profiles/r02_gemm_timeline.jsonl: 6.2 us of epilogue per 128 x 256 tile against 4.2-4.8 us of MMAs); packing halves
@@ -206,6 +225,8 @@ __device__ __forceinline__ void gelu_cdf2(float u0, float u1, unsigned long long
   float s0, s1;
   f2_unpack(s, s0, s1);
   const unsigned long long sc = f2_pack(fminf(s0, 16.0f), fminf(s1, 16.0f));
+  // Horner: an Estrin split (dependency depth 4 instead of 8) was measured SLOWER here — 2.0 instead of 1.5 us of
+  // math per 64-column chunk: the epilogue is bound by the fp32 pipe and by registers, not by the FMA latency chain
   unsigned long long p = FV_F2C(3.463219783e-01f / 4294967296.0f);
   p = f2_fma(p, sc, FV_F2C(-1.879982349e+00f / 268435456.0f));
   p = f2_fma(p, sc, FV_F2C(4.556960448e+00f / 16777216.0f));

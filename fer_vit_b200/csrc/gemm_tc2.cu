@@ -78,9 +78,13 @@ struct Cfg {
   static constexpr int WARP_STAGING = X_BYTES + Y_BYTES + Z_BYTES;
   static constexpr int STAGING = ALIAS ? 0 : EPI_WARPS * WARP_STAGING;   // bytes of shared memory of its own
   static constexpr int BAR_BYTES = 512;
-  static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - STAGING;
+  // bias of the tile in flight, staged once per tile by the epilogue warps (2 column halves x 128 floats): the chunk
+  // loop then reads it with broadcast shared-memory loads instead of paying a global-load latency per chunk
+  // (0.5-0.65 us of every 64-column chunk, profiles/r02_gemm_phase_timeline_before.jsonl)
+  static constexpr int BIAS_BYTES = 1024;
+  static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - STAGING;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + 1024;  // +1024: manual alignment
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + BIAS_BYTES + 1024;  // +1024: alignment
   static_assert(!ALIAS || EPI_WARPS * WARP_STAGING <= STAGES * STAGE_BYTES, "aliased staging must fit in the ring");
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator buffers; 256 or 512 (powers of two)
   static_assert(STAGES >= (F32 == 2 ? 2 : 3), "pipeline too shallow");
@@ -118,6 +122,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint64_t* tmem_empty = bars + 2 * C::STAGES + 2;   // [2]        leader's is the live one
   uint64_t* ld_bar = bars + 2 * C::STAGES + 4;       // [EPI_WARPS][4]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4 + 4 * EPI_WARPS);
+  float* sbias_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::STAGING + C::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -342,6 +347,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
       if (p.debug & 4) nch = 0;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * BN + c_lo * CW);
+      // stage this unit's bias (the 128 columns of this warp's half) while the MMAs of the tile are still running;
+      // the four warps of a column half share it: barrier 2 + half, once before (the previous tile's reads are done)
+      // and once after the write
+      const float* sb = sbias_all + half * 128;
+      if (p.bias) {
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+        const int ci = quarter * 32 + lane;
+        const int gc = t.n_blk * BN + t.col_off + c_lo * CW + ci;
+        sbias_all[half * 128 + ci] = (ci < per_half * CW && gc < p.N) ? __ldg(p.bias + gc) : 0.0f;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
+      }
 
       if constexpr (F32) {
         // ------------------------------------------------------------------------------------------------
@@ -412,10 +428,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
           }
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+            const float4* b4 = reinterpret_cast<const float4*>(sb + j * CW);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 bb = __ldg(b4 + i);
+              const float4 bb = b4[i];
               v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w;
             }
           }
@@ -531,10 +547,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
             }
           }
           if (p.bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+            const float4* b4 = reinterpret_cast<const float4*>(sb + j * CW);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float4 bb = __ldg(b4 + i);
+              const float4 bb = b4[i];
               f2_unpack(f2_add(f2_pack(v[4 * i], v[4 * i + 1]), f2_pack(bb.x, bb.y)), v[4 * i], v[4 * i + 1]);
               f2_unpack(f2_add(f2_pack(v[4 * i + 2], v[4 * i + 3]), f2_pack(bb.z, bb.w)), v[4 * i + 2], v[4 * i + 3]);
             }

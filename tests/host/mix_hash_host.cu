@@ -35,6 +35,20 @@ int main(int argc, char** argv) {
     }
     printf("G %.3e %.3e %.3e %.3e\n", e_in, e_tail, d_in, d_tail);
   }
+  {  // the packed (FFMA2) forward epilogue: one min on u^2 + saturating cdf, value and derivative in one pass
+    double e_in = 0, e_tail = 0, d_in = 0, d_tail = 0;
+    for (int i = -80000; i <= 80000; ++i) {
+      const double u = i * 1e-4;
+      const double cdf = 0.5 * (1.0 + erf(u / sqrt(2.0)));
+      const double g = u * cdf, d = cdf + u * exp(-0.5 * u * u) / sqrt(2.0 * 3.14159265358979323846);
+      float gg, dd;
+      fervit::gelu_fwd_deriv_packed_mirror((float)u, gg, dd);
+      const double eg = fabs((double)gg - g), ed = fabs((double)dd - d);
+      if (fabs(u) <= 4.0) { if (eg > e_in) e_in = eg; if (ed > d_in) d_in = ed; }
+      else { if (eg > e_tail) e_tail = eg; if (ed > d_tail) d_tail = ed; }
+    }
+    printf("E %.3e %.3e %.3e %.3e\n", e_in, e_tail, d_in, d_tail);
+  }
   printf("T %u %u %u\n", fervit::drop_threshold(0.1f), fervit::drop_threshold(0.5f), fervit::drop_threshold(0.999f));
   return 0;
 }

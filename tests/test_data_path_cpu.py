@@ -202,7 +202,11 @@ def test_generator_restatement_matches_the_c_source(tmp_path):
     # (absolute; |gelu| error inside the clamp is u * 7e-6 <= 2.8e-5)
     g_in, g_tail, d_in, d_tail = (float(v) for v in lines[len(cases) + 2].split()[1:])
     assert g_in < 3e-5 and g_tail < 3e-4 and d_in < 7e-5 and d_tail < 6e-4, (g_in, g_tail, d_in, d_tail)
-    thr = [int(v) for v in lines[len(cases) + 3].split()[1:]]
+    # the packed forward epilogue (min on u^2 + saturating cdf; value and derivative): |u| > 4 is exact to the cdf's tail
+    e_in, e_tail, ed_in, ed_tail = (float(v) for v in lines[len(cases) + 3].split()[1:])
+    assert lines[len(cases) + 3].startswith("E ")
+    assert e_in < 3e-5 and e_tail < 3e-4 and ed_in < 3e-5 and ed_tail < 3e-4, (e_in, e_tail, ed_in, ed_tail)
+    thr = [int(v) for v in lines[len(cases) + 4].split()[1:]]
     assert thr == [int(float(np.float32(p)) * 4294967296.0) for p in (0.1, 0.5, 0.999)]
 
 
