@@ -68,6 +68,7 @@ SIGNATURES = {
     "fervit_plan_num_slots": (_i, [_p]),
     "fervit_plan_slot_numel": (_ll, [_p, _i]),
     "fervit_plan_set_params": (_i, [_p, C.POINTER(_p), _i]),
+    "fervit_plan_set_ln_fold": (_i, [_p, C.POINTER(_i), C.POINTER(_i), _i]),
     "fervit_plan_wcache_bytes": (_ll, [_p]),
     "fervit_plan_set_wcache": (_i, [_p, _p, _ll]),
     "fervit_plan_refresh_wcache": (_i, [_p, C.POINTER(_i), _i, _p]),

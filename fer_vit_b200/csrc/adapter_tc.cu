@@ -52,6 +52,10 @@ struct Params {
   bf16* s0;                // [T, 64] forward: g;  backward: du
   bf16* s1;                // [T, 64] forward: d;  backward: unused
   int has_out_bf16;
+  // folded LayerNorm, producer side (common.cuh: Epilogue): the rows of `out` are the input of the next block's norm1;
+  // the bf16 copy becomes bf16(y - mref[row]) and each warp writes the {sum, sum of squares} of its 128-column part
+  float* lnp_part;
+  const float* lnp_mref;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -235,6 +239,8 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const uint32_t xsw = (uint32_t)(r & 7), ysw = (uint32_t)((r >> 1) & 3);
       uint32_t rr[32];
       tmem_ld32(taddr0, rr);
+      float ln_s1 = 0.f, ln_s2 = 0.f;
+      const float ln_mr = (p.lnp_part && p.lnp_mref && row < p.T) ? __ldg(p.lnp_mref + row) : 0.f;
 #pragma unroll 1
       for (int j = 0; j < 4; ++j) {
         const int b = j & 1;
@@ -267,6 +273,14 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           v[4 * c] += x.x; v[4 * c + 1] += x.y; v[4 * c + 2] += x.z; v[4 * c + 3] += x.w;
           *reinterpret_cast<float4*>(q) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
+        if (p.lnp_part) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v[i] -= ln_mr;
+            ln_s1 += v[i];
+            ln_s2 = fmaf(v[i], v[i], ln_s2);
+          }
+        }
         if (p.has_out_bf16) {
           uint8_t* yrow = Ys + b * YT + r * 64;
 #pragma unroll
@@ -288,6 +302,8 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
       }
       if (lane == 0) tma_store_wait_read<0>();
+      if (p.lnp_part && row < p.T)
+        reinterpret_cast<float2*>(p.lnp_part)[(size_t)row * (p.E >> 7) + (col_base >> 7)] = make_float2(ln_s1, ln_s2);
     }
   }
 
@@ -311,7 +327,8 @@ bool adapter_fused_supported(int T, int E, int A) {
 //                          out = dx fp32 (+ out_bf16), d_in = d, s0 = du
 int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, const float* res, const float* b1,
                   const float* b2, const float* alpha_ptr, const bf16* d_in, bf16* s0, bf16* s1, float* out,
-                  bf16* out_bf16, int T, int E, cudaStream_t stream) {
+                  bf16* out_bf16, int T, int E, cudaStream_t stream, float* lnp_part, const float* lnp_mref) {
+  FV_CHECK(!lnp_part || (out_bf16 && !backward), "adapter_fused: a LayerNorm producer is a forward pass with a bf16 copy");
   FV_CHECK(adapter_fused_supported(T, E, adp::AD), "adapter_fused: unsupported shape T=%d E=%d", T, E);
   FV_CHECK(in && Aw && Bw && res && alpha_ptr && s0 && out, "adapter_fused: null argument");
   FV_CHECK(backward ? (d_in != nullptr) : (b1 && b2 && s1), "adapter_fused: missing operand for this direction");
@@ -327,6 +344,7 @@ int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, 
   p.T = T; p.E = E; p.groups = E / adp::NC; p.backward = backward;
   p.b1 = b1; p.b2 = b2; p.alpha_ptr = alpha_ptr; p.d_in = d_in; p.s0 = s0; p.s1 = s1;
   p.has_out_bf16 = out_bf16 != nullptr;
+  p.lnp_part = lnp_part; p.lnp_mref = lnp_mref;
   static bool attr_set = false;
   if (!attr_set) {
     FV_CUDA(cudaFuncSetAttribute(adp::adapter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, adp::SMEM_BYTES));

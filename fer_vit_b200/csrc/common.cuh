@@ -362,6 +362,23 @@ struct Epilogue {
   Dropout drop;
   void* sk_ws;             // stream-K scratch of the CTA-pair GEMM (gemm_tc2.cu), zero-initialised flags first; or null
   size_t sk_bytes;
+  // ---- LayerNorm folded into the GEMMs either side of it (bf16 mode, frozen norm + frozen weight) ----
+  // y = LN(x) W^T + b with LN(x) = (x - mu) rstd gamma + beta is computed as
+  //     y_j = rstd * (acc_j - delta * cs_j) + b'_j,   acc = A W'^T,  A = bf16(x - mref),  W' = W diag(gamma),
+  //     delta = mu - mref,  cs_j = sum_k W'_jk (of the bf16-rounded W'),  b' = b + W beta  (passed as `bias`).
+  // CONSUMER (this GEMM applies the norm): the row statistics come from per-128-column partial sums the producer
+  // left; the exact mean / rstd are written out for the LayerNorm backward.
+  const float* ln_part;    // [M, ln_parts, 2] {sum, sum of squares} of (x - mref) per 128-column part; null = no fold
+  const float* ln_mref;    // [M] what the producer subtracted (null = 0)
+  const float* ln_cs;      // [N]
+  float* ln_mean;          // [M] out
+  float* ln_rstd;          // [M] out
+  float ln_eps;
+  int ln_parts;            // E / 128
+  // PRODUCER (this GEMM's fp32 output rows are the input of a folded norm): `out` receives bf16(v - mref[row]) and
+  // the partial sums of this GEMM's 128-column parts are written (each exactly once: deterministic)
+  float* lnp_part;         // [M, N / 128, 2] out; null = plain output
+  const float* lnp_mref;   // [M] or null
 };
 
 static inline Epilogue make_epilogue() {

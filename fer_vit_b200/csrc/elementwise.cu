@@ -79,6 +79,35 @@ __global__ void weight_cache_batch_kernel(const __grid_constant__ WcBatch b) {
   }
 }
 
+// ---- LayerNorm folded into the weight that follows it (frozen norm + frozen nn.Linear, bf16 mode) ----
+//   W'[j,k] = W[j,k] * gamma[k]  (bf16, also transposed),  b'[j] = b[j] + sum_k W[j,k] beta[k]  (fp32, unrounded W),
+//   cs[j] = sum_k float(bf16(W'[j,k]))  — the column sum the consumer's epilogue multiplies the row's mean shift by,
+//   taken over exactly the values the tensor core sees.
+// One warp per output row j; fixed summation order (deterministic). Runs when a frozen weight (re)enters the cache.
+__global__ void fold_ln_weight_kernel(const float* __restrict__ W, const float* __restrict__ b,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, int R, int C,
+                                      bf16* __restrict__ dst, bf16* __restrict__ dst_t, float* __restrict__ bfold,
+                                      float* __restrict__ cs) {
+  const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= R) return;
+  float sb = 0.f, sc = 0.f;
+  for (int k = lane; k < C; k += 32) {
+    const float w = W[(size_t)j * C + k];
+    const bf16 wf = __float2bfloat16_rn(w * gamma[k]);
+    dst[(size_t)j * C + k] = wf;
+    dst_t[(size_t)k * R + j] = wf;
+    sb = fmaf(w, beta[k], sb);
+    sc += __bfloat162float(wf);
+  }
+  sb = warp_sum(sb);
+  sc = warp_sum(sc);
+  if (lane == 0) {
+    bfold[j] = (b ? b[j] : 0.f) + sb;
+    cs[j] = sc;
+  }
+}
+
 // ---- im2col for stride == kernel patchify (image_vit.py:27-43): x [B,C,H,W] -> A [B*L, C*P*P] ----
 template <typename AT>
 __global__ void im2col_kernel(const float* __restrict__ x, AT* __restrict__ out, int B, int C, int H, int W,
@@ -379,6 +408,15 @@ int weight_cache_batch(const float* const* src, const int* R, const int* C, bf16
     FV_COUNT_LAUNCH();
     FV_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+int fold_ln_weight(const float* W, const float* b, const float* gamma, const float* beta, int R, int C, bf16* dst,
+                   bf16* dst_t, float* bfold, float* cs, cudaStream_t stream) {
+  FV_CHECK(W && gamma && beta && dst && dst_t && bfold && cs, "fold_ln_weight: null argument");
+  ew::fold_ln_weight_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(W, b, gamma, beta, R, C, dst, dst_t, bfold, cs);
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
   return 0;
 }
 

@@ -492,6 +492,8 @@ int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool
   // (wgrad), split-K, row-remapping and dropout epilogues
   if (!a_mn && !b_mn && p.splits == 1 && force_bn >= 0 && gemm_bf16_tc2_supported(M, N, K, lda, ldb, epi, kind))
     return gemm_bf16_tc2(A, lda, B, ldb, M, N, K, force_bn, epi, kind, stream);
+  FV_CHECK(!epi.ln_part && !epi.lnp_part, "gemm_bf16_tc: a folded LayerNorm needs the CTA-pair kernel, which does not "
+           "support this problem (M=%d N=%d K=%d)", M, N, K);
   if (force_bn < 0) force_bn = -force_bn;  // negative: force this kernel with that tile width (benchmarks)
   int bn = force_bn > 0 ? force_bn : tc::choose_bn(M, N, p.kb_per_split, p.splits);
   if (a_mn != b_mn) { set_error("gemm_bf16_tc: mixed operand major-ness is not instantiated"); return 1; }

@@ -379,6 +379,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         mbar_wait_cluster(&tmem_full[buf], acc_phase, 4);
         tc_fence_after();
         if (ew == 0 && lane == 0 && it < 4) TL(TL_ACC_READY + 2 * it);
+        float ln_s1 = 0.f, ln_s2 = 0.f, ln_mr = 0.f;   // folded-LayerNorm producer: partial sums of this row's part
+        if (p.lnp_part && p.lnp_mref && row0 + r < p.M) ln_mr = __ldg(p.lnp_mref + row0 + r);
         if (C::ALIAS && res && lane == 0 && nch > 0) {
           // single-tile form: the staging tiles alias the operand ring, free now that every MMA has completed
           for (int jj = 0; jj < nch && jj < (int)XB; ++jj) issue_load(g + jj, col0 + jj * CW);
@@ -458,6 +460,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               *reinterpret_cast<float4*>(xrow + ((c ^ xsw) << 4)) =
                   make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           }
+          if (p.lnp_part) {
+            // the bf16 copy is the A operand of the GEMM that applies the LayerNorm: centred on the row's reference
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] -= ln_mr;
+              ln_s1 += v[i];
+              ln_s2 = fmaf(v[i], v[i], ln_s2);
+            }
+          }
           if (p.has_out) {
             uint8_t* yrow = Ys + yb * YT + r * 64;
 #pragma unroll
@@ -480,6 +491,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           if (tlc) TL(TL_CHUNK + 6 * j + 5);
         }
+        if (p.lnp_part && row0 + r < p.M) {
+          // this warp covered one 128-column part of its rows: {sum, sum of squares} of (v - mref), written once
+          float2* dst = reinterpret_cast<float2*>(p.lnp_part) + (size_t)(row0 + r) * (p.N >> 7) + (col0 >> 7);
+          *dst = make_float2(ln_s1, ln_s2);
+        }
       } else {
         // ------------------------------------------------------------------------------------------------
         // bf16 kinds: 64-column chunks (128-byte rows, SWIZZLE_128B tiles), one store group per chunk
@@ -490,6 +506,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           mbar_expect_tx(&my_ld[b], YT2);
           tma_load_2d(Zs + b * YT2, &tm_z, &my_ld[b], col, row0);
         };
+        // folded LayerNorm, consumer side: this row's statistics from the producer's per-part sums (read while the
+        // MMAs of the tile are still running); y = lnA * acc + lnB * cs_j + b'_j
+        float lnA = 1.f, lnB = 0.f;
+        if (p.ln_part) {
+          const int row = row0 + r;
+          if (row < p.M) {
+            const float2* pp = reinterpret_cast<const float2*>(p.ln_part) + (size_t)row * p.ln_parts;
+            float sm = 0.f, sq = 0.f;
+            for (int k = 0; k < p.ln_parts; ++k) {   // fixed order
+              const float2 q2 = __ldg(pp + k);
+              sm += q2.x; sq += q2.y;
+            }
+            const float inv_e = 1.0f / (float)p.K;
+            const float dlt = sm * inv_e;                            // mu - mref
+            const float var = fmaxf(fmaf(-dlt, dlt, sq * inv_e), 0.f);
+            lnA = rsqrtf(var + p.ln_eps);
+            lnB = -lnA * dlt;
+            if (t.n_blk == 0 && t.col_off == 0 && half == 0) {        // one writer per row
+              p.ln_mean[row] = (p.ln_mref ? __ldg(p.ln_mref + row) : 0.f) + dlt;
+              p.ln_rstd[row] = lnA;
+            }
+          }
+        }
         if (C::BWD_ACT && lane == 0 && nch > 0) {
           // the pre-activation tiles of this output tile travel while its MMAs are still running
           issue_aux(g, col0);
@@ -546,7 +585,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               }
             }
           }
-          if (p.bias) {
+          if (p.ln_part) {
+            const float4* b4 = reinterpret_cast<const float4*>(sb + j * CW);
+            const float4* c4 = reinterpret_cast<const float4*>(p.ln_cs + col);
+            const unsigned long long a2 = f2_pack(lnA, lnA), b2 = f2_pack(lnB, lnB);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float4 bb = b4[i];
+              const float4 cc = __ldg(c4 + i);
+              f2_unpack(f2_fma(a2, f2_pack(v[4 * i], v[4 * i + 1]), f2_fma(b2, f2_pack(cc.x, cc.y), f2_pack(bb.x, bb.y))),
+                        v[4 * i], v[4 * i + 1]);
+              f2_unpack(f2_fma(a2, f2_pack(v[4 * i + 2], v[4 * i + 3]),
+                               f2_fma(b2, f2_pack(cc.z, cc.w), f2_pack(bb.z, bb.w))),
+                        v[4 * i + 2], v[4 * i + 3]);
+            }
+          } else if (p.bias) {
             const float4* b4 = reinterpret_cast<const float4*>(sb + j * CW);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -757,6 +810,19 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   FV_TRY(make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN / 2, 128));
   Params p;
   p.M = M; p.N = N; p.K = K;
+  p.ln_part = e.ln_part; p.ln_mref = e.ln_mref; p.ln_cs = e.ln_cs; p.ln_mean = e.ln_mean; p.ln_rstd = e.ln_rstd;
+  p.ln_eps = e.ln_eps; p.ln_parts = e.ln_parts;
+  p.lnp_part = e.lnp_part; p.lnp_mref = e.lnp_mref;
+  if (e.ln_part) {
+    FV_CHECK(F32 == 0 && (KIND == EPK_PLAIN || KIND == EPK_GELU || KIND == EPK_RELU), "folded LayerNorm: consumer must be "
+             "a bf16-output forward GEMM");
+    FV_CHECK(e.ln_cs && e.bias && e.ln_mean && e.ln_rstd && e.ln_parts > 0 && e.ln_parts <= 8 && K == 128 * e.ln_parts,
+             "folded LayerNorm: consumer needs cs, b', statistics outputs and K = 128 * parts (K=%d parts=%d)", K,
+             e.ln_parts);
+  }
+  if (e.lnp_part)
+    FV_CHECK(F32 != 0 && e.out != nullptr && e.out_f32 != nullptr && N % 128 == 0 && BN == 256,
+             "folded LayerNorm: producer must be an fp32-stream GEMM with a bf16 copy and N a multiple of 128");
   p.pair_m_blocks = ceil_div(M, 2 * BM);
   p.n_blocks = ceil_div(N, BN);
   p.bias = e.bias; p.alpha_ptr = e.alpha_ptr; p.alpha = e.alpha;
@@ -774,7 +840,7 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
     static int no_split = -1;
     if (no_split < 0) { const char* s = getenv("FERVIT_GEMM_NO_TAIL_SPLIT"); no_split = (s && atoi(s)) ? 1 : 0; }
     // only when complete rounds exist (otherwise there is no round to shorten) and the slices fit in one round
-    if (!no_split && p.full_units > 0 && rest > 0) {
+    if (!no_split && p.full_units > 0 && rest > 0 && !e.lnp_part) {   // producers write per-128-column partials
       const int min_w = 64;   // one 64-column chunk (bf16 kinds) / two 32-column chunks (fp32 kinds)
       if (rest * 4 <= max_pairs && BN / 4 >= min_w) p.split = 4;
       else if (rest * 2 <= max_pairs && BN / 2 >= min_w) p.split = 2;

@@ -42,6 +42,10 @@ struct Params {
   // in-kernel launch timer (fervit_gemm_prof): {min over CTAs of %globaltimer once the grid dependency has resolved,
   // max over CTAs at exit}; null = off. Works inside CUDA-graph replays, where host-side events cannot sit.
   unsigned long long* prof;
+  // folded LayerNorm (common.cuh: Epilogue): consumer and producer side
+  const float* ln_part; const float* ln_mref; const float* ln_cs; float* ln_mean; float* ln_rstd;
+  float ln_eps; int ln_parts;
+  float* lnp_part; const float* lnp_mref;
 };
 
 

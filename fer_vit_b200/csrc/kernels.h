@@ -25,7 +25,8 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, u
 bool adapter_fused_supported(int T, int E, int A);
 int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, const float* res, const float* b1,
                   const float* b2, const float* alpha_ptr, const bf16* d_in, bf16* s0, bf16* s1, float* out,
-                  bf16* out_bf16, int T, int E, cudaStream_t stream);
+                  bf16* out_bf16, int T, int E, cudaStream_t stream, float* lnp_part = nullptr,
+                  const float* lnp_mref = nullptr);
 // gemm_simt.cu
 int gemm_f32_simt(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk, int M,
                   int N, int K, int splits, const Epilogue& epi, cudaStream_t stream);
@@ -46,6 +47,9 @@ template <typename AT> int cast_to_act(const float* src, AT* dst, size_t n, cuda
 int weight_cache(const float* src, int R, int C, bf16* dst, bf16* dst_t, cudaStream_t stream);
 int weight_cache_batch(const float* const* src, const int* R, const int* C, bf16* const* dst, bf16* const* dst_t, int n,
                        cudaStream_t stream);
+// W' = W diag(gamma) (bf16 + transposed), b' = b + W beta, cs = column sums of bf16 W' (LayerNorm folded into nn.Linear)
+int fold_ln_weight(const float* W, const float* b, const float* gamma, const float* beta, int R, int C, bf16* dst,
+                   bf16* dst_t, float* bfold, float* cs, cudaStream_t stream);
 template <typename AT> int im2col(const float* x, AT* out, int B, int C, int H, int W, int P, cudaStream_t stream);
 template <typename AT>
 int cls_rows(const float* cls, const float* pos, float* x0, AT* x0_at, int B, int S, int E, Dropout drop,

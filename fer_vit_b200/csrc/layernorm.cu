@@ -204,7 +204,8 @@ ln_bwd_pair_kernel(const DT* __restrict__ dy, const float* __restrict__ x, const
     for (int i = 0; i < CHH; ++i) {
       const int c = lane * 4 + (hw * CHH + i) * 128;
       if (c < E) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        // gamma == nullptr: the norm's scale was folded into the weight that follows it, dy already is gamma * dh
+        const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(1.f, 1.f, 1.f, 1.f);
         xv[i] = make_float4((xv[i].x - mu) * rs, (xv[i].y - mu) * rs, (xv[i].z - mu) * rs, (xv[i].w - mu) * rs);  // xhat
         dv[i] = make_float4(dv[i].x * g.x, dv[i].y * g.y, dv[i].z * g.z, dv[i].w * g.w);                          // g * dy
         s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
@@ -278,6 +279,8 @@ int layernorm_bwd(const DT* dy, const float* x, const float* mean, const float* 
                   cudaStream_t stream) {
   FV_CHECK(E % 4 == 0 && E <= 1024, "layernorm: E must be a multiple of 4 and <= 1024 (got %d)", E);
   if (rows <= 0) return 0;
+  FV_CHECK(gamma != nullptr || (partial == nullptr && !at_drop.threshold),
+           "layernorm_bwd: a folded (null) gamma is only defined for the streaming form (no parameter gradients)");
   // algorithmic bytes: read dy and x (and dres), write each requested output, 8 B of statistics per row
   ProfScope prof(2, (double)rows * E * ((double)sizeof(DT) + 4.0 + (dres ? 4.0 : 0.0) + (dx_f32 ? 4.0 : 0.0) +
                                         (dx_at ? (double)sizeof(AT) : 0.0)) + rows * 8.0, stream);

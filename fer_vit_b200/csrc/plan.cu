@@ -54,6 +54,7 @@ struct Bufs {
   std::vector<BlockBufs> blk;
   float *head_mean, *head_rstd;
   float* tmp_f32;              // [T,E]
+  float* ln_part[2];           // folded LayerNorm: per-row, per-128-column {sum, sum of squares}; [0] norm1, [1] norm2
   // backward transients
   float* dx[2];
   void* dx_at[2];
@@ -87,6 +88,12 @@ struct fervit_plan {
   size_t wcache_bytes;
   char* wcache;
   size_t sk_off = SIZE_MAX, sk_bytes = 0;  // stream-K scratch of the CTA-pair GEMM, inside the weight cache buffer
+  // LayerNorm folded into the GEMM that follows it (frozen norm + frozen weight, bf16 mode): per block,
+  // norm1 -> qkv and norm2 -> fc1. The weight cache then holds W diag(gamma) for those slots, plus b' and cs.
+  std::vector<int> fold1, fold2;
+  std::vector<size_t> fb_off, fcs_off;     // per slot: byte offsets of b' [out] and cs [out] (fp32) in the weight cache
+  const float* FB(int slot) const { return reinterpret_cast<const float*>(wcache + fb_off[slot]); }
+  const float* FCS(int slot) const { return reinterpret_cast<const float*>(wcache + fcs_off[slot]); }
   int bwd_cur;  // which of dx[0]/dx[1] holds the running gradient between backward stages
   // Side stream of the backward pass: the adapter weight-gradient GEMMs and column sums do not feed the dgrad chain,
   // so they run beside it and fill the SMs the chain leaves idle (57-tile GEMMs, partial last waves). Fork/join by
@@ -257,6 +264,11 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
   b.head_mean = ar.take<float>(B);
   b.head_rstd = ar.take<float>(B);
   b.tmp_f32 = ar.take<float>(T * E);
+  b.ln_part[0] = b.ln_part[1] = nullptr;
+  if (bf && !post && E % 128 == 0) {
+    b.ln_part[0] = ar.take<float>(T * (E / 128) * 2);
+    b.ln_part[1] = ar.take<float>(T * (E / 128) * 2);
+  }
   if (save) {
     for (int i = 0; i < 2; ++i) {
       b.dx[i] = ar.take<float>(T * E);
@@ -440,22 +452,40 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
   for (int i = 0; i < c.depth; ++i) {
     BlockBufs& k = b.blk[i];
     if (!post) {
-      FV_TRY(layernorm_fwd<AT>(b.x[i], p->PB(i, FERVIT_B_LN1_W), p->PB(i, FERVIT_B_LN1_B), c.eps_block, T, E, nullptr,
-                               (AT*)k.xn1, k.m1, k.r1, st));
+      // Folded LayerNorms (frozen norm + frozen weight, bf16 mode): no norm kernel. The GEMM that PRODUCES the norm's
+      // input also writes its bf16 copy centred on the row's previous mean and the per-part sums; the GEMM that
+      // CONSUMES it applies rstd, the mean shift and the folded bias in its epilogue (common.cuh: Epilogue).
+      const bool f1 = !F32 && p->fold1[i], f2 = !F32 && p->fold2[i];
+      const bool f1_next = !F32 && i + 1 < c.depth && p->fold1[i + 1];
+      const int qkv_slot = p->bslot(i, FERVIT_B_QKV_W), fc1_slot = p->bslot(i, FERVIT_B_FC1_W);
+      if (!f1)
+        FV_TRY(layernorm_fwd<AT>(b.x[i], p->PB(i, FERVIT_B_LN1_W), p->PB(i, FERVIT_B_LN1_B), c.eps_block, T, E, nullptr,
+                                 (AT*)k.xn1, k.m1, k.r1, st));
       Epilogue e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_QKV_B); e.out = k.qkv; e.ldo = 3 * E;
-      FV_TRY(linear<AT>(cx, (const AT*)k.xn1, T, p->bslot(i, FERVIT_B_QKV_W), false, e));
+      if (f1) {
+        e.bias = p->FB(qkv_slot); e.ln_cs = p->FCS(qkv_slot); e.ln_part = b.ln_part[0]; e.ln_mref = b.blk[i - 1].m2;
+        e.ln_mean = k.m1; e.ln_rstd = k.r1; e.ln_eps = c.eps_block; e.ln_parts = E / 128;
+      }
+      FV_TRY(linear<AT>(cx, (const AT*)k.xn1, T, qkv_slot, false, e));
       FV_TRY(attention_fwd<AT>((const AT*)k.qkv, (AT*)k.ao, k.lse, B, S, c.H, p->HD, cx.site(i, 0), st));
       e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_PROJ_B); e.residual = b.x[i]; e.out_f32 = k.x_mid; e.ldo = E; e.drop = cx.site(i, 1);
+      if (f2) { e.out = k.xn2; e.lnp_part = b.ln_part[1]; e.lnp_mref = k.m1; }
       FV_TRY(linear<AT>(cx, (const AT*)k.ao, T, p->bslot(i, FERVIT_B_PROJ_W), false, e));
-      FV_TRY(layernorm_fwd<AT>(k.x_mid, p->PB(i, FERVIT_B_LN2_W), p->PB(i, FERVIT_B_LN2_B), c.eps_block, T, E, nullptr,
-                               (AT*)k.xn2, k.m2, k.r2, st));
+      if (!f2)
+        FV_TRY(layernorm_fwd<AT>(k.x_mid, p->PB(i, FERVIT_B_LN2_W), p->PB(i, FERVIT_B_LN2_B), c.eps_block, T, E, nullptr,
+                                 (AT*)k.xn2, k.m2, k.r2, st));
       e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_FC1_B); e.act = c.act; e.out_pre = k.u1; e.pre_is_deriv = 1; e.out = k.g1; e.ldo = F; e.drop = cx.site(i, 2);
-      FV_TRY(linear<AT>(cx, (const AT*)k.xn2, T, p->bslot(i, FERVIT_B_FC1_W), false, e));
+      if (f2) {
+        e.bias = p->FB(fc1_slot); e.ln_cs = p->FCS(fc1_slot); e.ln_part = b.ln_part[1]; e.ln_mref = k.m1;
+        e.ln_mean = k.m2; e.ln_rstd = k.r2; e.ln_eps = c.eps_block; e.ln_parts = E / 128;
+      }
+      FV_TRY(linear<AT>(cx, (const AT*)k.xn2, T, fc1_slot, false, e));
       e = make_epilogue();
       e.bias = p->PB(i, FERVIT_B_FC2_B); e.residual = k.x_mid; e.ldo = E; e.drop = cx.site(i, 3);
+      void* next_xn1 = f1_next ? b.blk[i + 1].xn1 : nullptr;   // where the next block's (folded) norm1 input goes
       if (A) {
         float* x2 = F32 ? (float*)k.x2_at : b.tmp_f32;
         e.out_f32 = x2;
@@ -468,7 +498,8 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
             FV_TRY(adapter_fused(0, (const bf16*)k.x2_at, p->WB(p->bslot(i, FERVIT_B_AD1_W)),
                                  p->WB(p->bslot(i, FERVIT_B_AD2_W)), x2, p->PB(i, FERVIT_B_AD1_B),
                                  p->PB(i, FERVIT_B_AD2_B), p->PB(i, FERVIT_B_ALPHA), nullptr, (bf16*)k.ga, (bf16*)k.ua,
-                                 b.x[i + 1], nullptr, T, E, st));
+                                 b.x[i + 1], (bf16*)next_xn1, T, E, st, f1_next ? b.ln_part[0] : nullptr,
+                                 f1_next ? k.m2 : nullptr));
             fused = true;
           }
         }
@@ -479,10 +510,12 @@ int forward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_b
           Epilogue u = make_epilogue();
           u.bias = p->PB(i, FERVIT_B_AD2_B); u.alpha_ptr = p->PB(i, FERVIT_B_ALPHA); u.residual = x2;
           u.out_f32 = b.x[i + 1]; u.ldo = E;
+          if (f1_next) { u.out = next_xn1; u.lnp_part = b.ln_part[0]; u.lnp_mref = k.m2; }
           FV_TRY(linear<AT>(cx, (const AT*)k.ga, T, p->bslot(i, FERVIT_B_AD2_W), false, u));
         }
       } else {
         e.out_f32 = b.x[i + 1];
+        if (f1_next) { e.out = next_xn1; e.lnp_part = b.ln_part[0]; e.lnp_mref = k.m2; }
         FV_TRY(linear<AT>(cx, (const AT*)k.g1, T, p->bslot(i, FERVIT_B_FC2_W), false, e));
       }
     } else {
@@ -639,7 +672,9 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
         {
           float* part = GB(i, FERVIT_B_LN2_W) ? b.scratch : nullptr;
-          FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, k.x_mid, k.m2, k.r2, p->PB(i, FERVIT_B_LN2_W), DX(cur), T, E,
+          // a folded norm2: fc1's cached transpose is (W diag(gamma))^T, so d_e1 already is gamma * dh
+          const float* g2 = (!F32 && p->fold2[i]) ? nullptr : p->PB(i, FERVIT_B_LN2_W);
+          FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, k.x_mid, k.m2, k.r2, g2, DX(cur), T, E,
                                         DX(cur ^ 1), ATOUT(cur ^ 1), part, nodrop, st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
@@ -673,7 +708,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         FV_TRY(linear<AT>(cx, (const AT*)b.d_big, T, p->bslot(i, FERVIT_B_QKV_W), true, e));
         {
           float* part = GB(i, FERVIT_B_LN1_W) ? b.scratch : nullptr;
-          FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, b.x[i], k.m1, k.r1, p->PB(i, FERVIT_B_LN1_W), DX(cur), T, E,
+          const float* g1 = (!F32 && p->fold1[i]) ? nullptr : p->PB(i, FERVIT_B_LN1_W);
+          FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, b.x[i], k.m1, k.r1, g1, DX(cur), T, E,
                                         DX(cur ^ 1), ATOUT(cur ^ 1), part, nodrop, st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
@@ -850,6 +886,25 @@ FV_API int fervit_plan_create(const fervit_config* cfg, fervit_plan** out) {
       }
     }
   }
+  p->fold1.assign(c.depth, 0);
+  p->fold2.assign(c.depth, 0);
+  p->fb_off.assign(p->nslots(), SIZE_MAX);
+  p->fcs_off.assign(p->nslots(), SIZE_MAX);
+  if (c.mode == FERVIT_BF16 && c.norm_first) {
+    for (int i = 0; i < c.depth; ++i) {
+      const int slots[2] = {fervit_plan::bslot(i, FERVIT_B_QKV_W), fervit_plan::bslot(i, FERVIT_B_FC1_W)};
+      for (int s : slots) {
+        int R, C;
+        if (!weight_shape(p, s, &R, &C)) continue;
+        off = (off + 255) & ~size_t(255);
+        p->fb_off[s] = off;
+        off += (size_t)R * 4;
+        off = (off + 255) & ~size_t(255);
+        p->fcs_off[s] = off;
+        off += (size_t)R * 4;
+      }
+    }
+  }
   if (c.mode == FERVIT_BF16) {
     off = (off + 255) & ~size_t(255);
     p->sk_off = off;
@@ -909,6 +964,19 @@ FV_API int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n
     int R, C;
     if (!weight_shape(plan, s, &R, &C)) return 0;
     FV_CHECK(plan->params[s] != nullptr, "refresh_wcache: parameter slot %d not set", s);
+    if (s >= FERVIT_NUM_GLOBAL) {
+      const int blk = (s - FERVIT_NUM_GLOBAL) / FERVIT_NUM_BLOCK, w = (s - FERVIT_NUM_GLOBAL) % FERVIT_NUM_BLOCK;
+      const bool f1 = w == FERVIT_B_QKV_W && plan->fold1[blk], f2 = w == FERVIT_B_FC1_W && plan->fold2[blk];
+      if (f1 || f2) {   // W diag(gamma), b + W beta, column sums: the norm in front of this weight is folded into it
+        const float* g = plan->PB(blk, f1 ? FERVIT_B_LN1_W : FERVIT_B_LN2_W);
+        const float* be = plan->PB(blk, f1 ? FERVIT_B_LN1_B : FERVIT_B_LN2_B);
+        const float* bias = plan->PB(blk, f1 ? FERVIT_B_QKV_B : FERVIT_B_FC1_B);
+        FV_CHECK(g && be && bias, "refresh_wcache: a folded LayerNorm needs its parameters and the bias bound");
+        return fold_ln_weight(plan->P(s), bias, g, be, R, C, const_cast<bf16*>(plan->WB(s)),
+                              const_cast<bf16*>(plan->WBT(s)), const_cast<float*>(plan->FB(s)),
+                              const_cast<float*>(plan->FCS(s)), st);
+      }
+    }
     src.push_back(plan->P(s));
     dst.push_back(const_cast<bf16*>(plan->WB(s)));
     dst_t.push_back(const_cast<bf16*>(plan->WBT(s)));
@@ -926,6 +994,24 @@ FV_API int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n
   }
   if (src.empty()) return 0;
   return weight_cache_batch(src.data(), Rs.data(), Cs.data(), dst.data(), dst_t.data(), (int)src.size(), st);
+}
+
+FV_API int fervit_plan_set_ln_fold(fervit_plan* plan, const int* fold_norm1, const int* fold_norm2, int depth) {
+  FV_CHECK(plan && fold_norm1 && fold_norm2, "set_ln_fold: null argument");
+  const fervit_config& c = plan->cfg;
+  FV_CHECK(depth == c.depth, "set_ln_fold: expected %d blocks, got %d", c.depth, depth);
+  bool any = false;
+  for (int i = 0; i < depth; ++i) any = any || fold_norm1[i] || fold_norm2[i];
+  if (any) {
+    FV_CHECK(c.mode == FERVIT_BF16 && c.norm_first, "set_ln_fold: folding is defined for bf16-mode pre-norm blocks only");
+    FV_CHECK(c.E % 128 == 0 && c.E <= 1024, "set_ln_fold: embed dim %d must be a multiple of 128 (<= 1024)", c.E);
+    FV_CHECK(!fold_norm1[0], "set_ln_fold: block 0's norm1 reads the token projection's output and stays a kernel");
+  }
+  for (int i = 0; i < depth; ++i) {
+    plan->fold1[i] = fold_norm1[i] ? 1 : 0;
+    plan->fold2[i] = fold_norm2[i] ? 1 : 0;
+  }
+  return 0;
 }
 
 FV_API long long fervit_plan_workspace_bytes(const fervit_plan* plan, int B, int save_for_backward) {

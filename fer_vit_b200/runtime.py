@@ -7,6 +7,7 @@ libfervit_b200.so on ``torch.cuda.current_stream()``; there is no PyTorch-op or 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -111,6 +112,7 @@ class PlanRunner:
             self._ptrs = key  # stale cache entries are detected per slot below (data_ptr, version)
         if self.bf16:
             dev = next(iter(tensors.values())).device
+            self._update_ln_fold(tensors)
             if self._wcache is None or self._wcache.device != dev:
                 nbytes = int(self._lib.fervit_plan_wcache_bytes(self._h))
                 self._wcache = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
@@ -122,7 +124,7 @@ class PlanRunner:
                 t = tensors.get(s)
                 if t is None:
                     continue
-                st = (t.data_ptr(), t._version)
+                st = (t.data_ptr(), t._version) + self._fold_state(s, tensors)
                 # frozen weights: re-cast when (data_ptr, version) moved (load_state_dict, manual edits). Trainable
                 # weights: re-cast on EVERY call — fused optimizers (torch.optim.AdamW(fused=True)) update parameters
                 # without bumping the version counter, and under CUDA-graph capture the host sees no update at all,
@@ -133,6 +135,44 @@ class PlanRunner:
             if stale:
                 arr = (C.c_int * len(stale))(*stale)
                 L.check(self._lib.fervit_plan_refresh_wcache(self._h, arr, len(stale), _stream_ptr()))
+
+    # ------------------------------------------------------------------ LayerNorm folding
+    def _update_ln_fold(self, tensors: Dict[int, torch.Tensor]) -> None:
+        """Frozen norm + frozen weight behind it => the norm is folded into that GEMM (include/fervit_b200.h:
+        fervit_plan_set_ln_fold). Decided per block from requires_grad; FERVIT_LN_FOLD=0 switches it off."""
+        d = self.depth
+        f1, f2 = [0] * d, [0] * d
+        cfg = self.cfg
+        on = os.environ.get("FERVIT_LN_FOLD", "1") != "0"
+        if on and cfg.norm_first and cfg.E % 128 == 0 and cfg.E <= 1024:
+            def frozen(blk, names):
+                return all((L.bslot(blk, n) in tensors) and not tensors[L.bslot(blk, n)].requires_grad for n in names)
+            for i in range(d):
+                f1[i] = int(i > 0 and frozen(i, (L.B_LN1_W, L.B_LN1_B, L.B_QKV_W, L.B_QKV_B)))
+                f2[i] = int(frozen(i, (L.B_LN2_W, L.B_LN2_B, L.B_FC1_W, L.B_FC1_B)))
+        key = (tuple(f1), tuple(f2))
+        if key != getattr(self, "_fold_key", None):
+            L.check(self._lib.fervit_plan_set_ln_fold(self._h, (C.c_int * d)(*f1), (C.c_int * d)(*f2), d))
+            self._fold_key = key
+            self.fold1, self.fold2 = f1, f2
+
+    def _fold_state(self, slot: int, tensors: Dict[int, torch.Tensor]) -> tuple:
+        """Extra cache-staleness key of a GEMM weight slot: a folded slot's cache entry also depends on the norm's
+        gamma / beta and on the bias."""
+        if slot < L.NUM_GLOBAL or not getattr(self, "_fold_key", None):
+            return ()
+        blk, w = divmod(slot - L.NUM_GLOBAL, L.NUM_BLOCK)
+        if w == L.B_QKV_W and self.fold1[blk]:
+            deps = (L.B_LN1_W, L.B_LN1_B, L.B_QKV_B)
+        elif w == L.B_FC1_W and self.fold2[blk]:
+            deps = (L.B_LN2_W, L.B_LN2_B, L.B_FC1_B)
+        else:
+            return ("plain",)
+        out = ["folded"]
+        for n in deps:
+            t = tensors[L.bslot(blk, n)]
+            out += [t.data_ptr(), t._version]
+        return tuple(out)
 
     # ------------------------------------------------------------------ workspaces
     def workspace_bytes(self, B: int, save: bool) -> int:

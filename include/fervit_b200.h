@@ -135,6 +135,15 @@ int fervit_plan_set_params(fervit_plan* plan, const void* const* params, int n);
 
 /* bf16 weight cache (W and W^T of every GEMM weight), a derived non-persistent copy that the caller owns and
  * refreshes after the optimizer changed the fp32 masters. slots == NULL refreshes every cached weight. */
+/* LayerNorm folding (bf16 mode, pre-norm blocks, E a multiple of 128): for every block whose norm1 (norm2) AND the
+ * qkv (fc1) weight and bias behind it are frozen, the norm is not run as a kernel. The weight cache then holds
+ * W diag(gamma) for that slot (+ b' = b + W beta and the column sums cs, fp32); the GEMM that produces the norm's input
+ * writes a bf16 copy centred on the row's previous mean plus per-128-column {sum, sum of squares}; the qkv / fc1 GEMM
+ * applies y = rstd (acc - (mu - mref) cs) + b' in its epilogue and saves mu / rstd for the backward pass, whose
+ * LayerNorm kernel then runs with gamma = 1 (the dgrad GEMM already multiplied by gamma). fold_norm1[0] must be 0
+ * (block 0's norm1 reads the token projection). Call before fervit_plan_refresh_wcache; changing a flag makes that
+ * slot's cache entry stale. Reference: timm Block.norm1 / norm2 called at hybrid_latent_vit.py:228. */
+int fervit_plan_set_ln_fold(fervit_plan* plan, const int* fold_norm1, const int* fold_norm2, int depth);
 long long fervit_plan_wcache_bytes(const fervit_plan* plan);
 int fervit_plan_set_wcache(fervit_plan* plan, void* ptr, long long bytes);
 int fervit_plan_refresh_wcache(fervit_plan* plan, const int* slots, int n, void* stream);

@@ -516,3 +516,66 @@ def test_graphed_step_with_dropout_bf16():
     losses = [float(stepper(x, y)) for _ in range(30)]
     assert all(map(lambda v: v == v and v < 1e3, losses))
     assert sum(losses[-5:]) / 5 < sum(losses[:5]) / 5 - 0.05, (losses[:5], losses[-5:])
+
+
+@pytest.mark.parametrize("size,E,heads", [("base", 768, 12), ("small", 384, 6)])
+def test_layernorm_fold_vs_unfolded_and_oracle(size, E, heads):
+    """Frozen norm1 / norm2 folded into the qkv / fc1 GEMMs (fervit_plan_set_ln_fold; bf16 mode): same logits and
+    gradients as the un-folded path within bf16 noise, both inside the 2e-2 gate against the fp64 oracle on the
+    non-zero-mean input distribution (the case that stresses the mean-shift term), and 23 kernel launches fewer per
+    forward (every norm except block 0's norm1). One block is then given a trainable norm1 and a trainable fc1 bias:
+    those two norms fall back to the kernel, their gradients appear and still match the oracle."""
+    import os
+    import fer_vit_b200 as fv
+    from fer_vit_b200 import _lib as L
+    from oracle import baseline_models as BM
+    from oracle import reference_math as R
+    fv.set_default_precision("bf16")
+    sd = BM.hybrid_state_dict(E=E, depth=12, heads=heads, seed=7)
+    model = fv.create_hybrid_latent_vit(model_size=size, use_pretrained=False, freeze_transformer=True, use_adapter=True,
+                                        adapter_dim=64)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(21)
+    B = 8
+    x = 0.5 * torch.randn(B, 18, 512, generator=g) + 0.3 * torch.randn(1, 18, 512, generator=g)
+    y = torch.randint(0, 7, (B,), generator=g)
+    BM.hybrid_trainable(sd)
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, heads, True, m), sd, x, y)
+    old = os.environ.get("FERVIT_LN_FOLD")
+    try:
+        out = {}
+        for flag in ("0", "1"):
+            os.environ["FERVIT_LN_FOLD"] = flag
+            step(model, x.cuda(), y.cuda())                      # cache refresh for this setting
+            n0 = L.launch_count()
+            with torch.no_grad():
+                model(x.cuda())
+            out[flag] = (step(model, x.cuda(), y.cuda()), L.launch_count() - n0)
+        (plain, n_plain), (folded, n_folded) = out["0"], out["1"]
+        runner = model.plan_runner()
+        assert sum(runner.fold1) == 11 and sum(runner.fold2) == 12
+        e_l = relerr(folded[0], plain[0])
+        e_g = max(relerr(folded[2][k], plain[2][k]) for k in plain[2] if not k.endswith(".alpha"))
+        record("layernorm_fold_vs_unfolded", size=size, err_logits=e_l, worst_grad=e_g)
+        assert e_l < 1e-2 and e_g < 2e-2, (e_l, e_g)
+        _compare(f"hybrid_{size}_ln_unfolded_vs_oracle", "bf16", plain, ref)
+        _compare(f"hybrid_{size}_ln_folded_vs_oracle", "bf16", folded, ref)
+        # forward + (forward + backward): 2 x 23 norm kernels fewer
+        assert n_plain - n_folded == 46, (n_plain, n_folded)
+        # per-parameter: a trainable norm1 weight in block 3 and a trainable fc1 bias in block 5 un-fold those two norms
+        named = dict(model.named_parameters())
+        named["transformer.3.norm1.weight"].requires_grad_(True)
+        named["transformer.5.mlp.fc1.bias"].requires_grad_(True)
+        sd["transformer.3.norm1.weight"].requires_grad_(True)
+        sd["transformer.5.mlp.fc1.bias"].requires_grad_(True)
+        ref2 = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, heads, True, m), sd, x, y)
+        got2 = step(model, x.cuda(), y.cuda())
+        assert runner.fold1[3] == 0 and runner.fold2[5] == 0 and sum(runner.fold1) == 10 and sum(runner.fold2) == 11
+        assert "transformer.3.norm1.weight" in got2[2] and "transformer.5.mlp.fc1.bias" in got2[2]
+        _compare(f"hybrid_{size}_ln_partly_folded_vs_oracle", "bf16", got2, ref2)
+    finally:
+        if old is None:
+            os.environ.pop("FERVIT_LN_FOLD", None)
+        else:
+            os.environ["FERVIT_LN_FOLD"] = old
