@@ -81,7 +81,9 @@ struct Cfg {
   // bias of the tile in flight, staged once per tile by the epilogue warps (2 column halves x 128 floats): the chunk
   // loop then reads it with broadcast shared-memory loads instead of paying a global-load latency per chunk
   // (0.5-0.65 us of every 64-column chunk, profiles/r02_gemm_phase_timeline_before.jsonl)
-  static constexpr int BIAS_BYTES = 1024;
+  // + 2 x 128 bf16: the folded-LayerNorm column sums cs (they multiply the small mean shift mu - mref, so bf16 is
+  // ample). 1536 bytes is exactly what is left beside 6 / 5 / 4 operand stages of the three staging layouts.
+  static constexpr int BIAS_BYTES = 1536;
   static constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - BIAS_BYTES - STAGING;
   static constexpr int STAGES = (AVAIL / STAGE_BYTES) > 8 ? 8 : (AVAIL / STAGE_BYTES);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING + BAR_BYTES + BIAS_BYTES + 1024;  // +1024: alignment
@@ -356,6 +358,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         const int ci = quarter * 32 + lane;
         const int gc = t.n_blk * BN + t.col_off + c_lo * CW + ci;
         sbias_all[half * 128 + ci] = (ci < per_half * CW && gc < p.N) ? __ldg(p.bias + gc) : 0.0f;
+        if (p.ln_part)
+          reinterpret_cast<bf16*>(sbias_all + 256)[half * 128 + ci] =
+              __float2bfloat16_rn((ci < per_half * CW && gc < p.N) ? __ldg(p.ln_cs + gc) : 0.0f);
         asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
       }
 
@@ -506,29 +511,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           mbar_expect_tx(&my_ld[b], YT2);
           tma_load_2d(Zs + b * YT2, &tm_z, &my_ld[b], col, row0);
         };
-        // folded LayerNorm, consumer side: this row's statistics from the producer's per-part sums (read while the
-        // MMAs of the tile are still running); y = lnA * acc + lnB * cs_j + b'_j
+        // folded LayerNorm, consumer side: y = lnA * acc + lnB * cs_j + b'_j with this row's lnA = rstd and
+        // lnB = -rstd * (mu - mref), derived from the producer's per-part sums at the first chunk (below)
         float lnA = 1.f, lnB = 0.f;
-        if (p.ln_part) {
-          const int row = row0 + r;
-          if (row < p.M) {
-            const float2* pp = reinterpret_cast<const float2*>(p.ln_part) + (size_t)row * p.ln_parts;
-            float sm = 0.f, sq = 0.f;
-            for (int k = 0; k < p.ln_parts; ++k) {   // fixed order
-              const float2 q2 = __ldg(pp + k);
-              sm += q2.x; sq += q2.y;
-            }
-            const float inv_e = 1.0f / (float)p.K;
-            const float dlt = sm * inv_e;                            // mu - mref
-            const float var = fmaxf(fmaf(-dlt, dlt, sq * inv_e), 0.f);
-            lnA = rsqrtf(var + p.ln_eps);
-            lnB = -lnA * dlt;
-            if (t.n_blk == 0 && t.col_off == 0 && half == 0) {        // one writer per row
-              p.ln_mean[row] = (p.ln_mref ? __ldg(p.ln_mref + row) : 0.f) + dlt;
-              p.ln_rstd[row] = lnA;
-            }
-          }
-        }
         if (C::BWD_ACT && lane == 0 && nch > 0) {
           // the pre-activation tiles of this output tile travel while its MMAs are still running
           issue_aux(g, col0);
@@ -550,6 +535,30 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           uint32_t ra[32], rb[32];
           tmem_ld32(taddr0 + (uint32_t)(j * CW), ra);
           tmem_ld32(taddr0 + (uint32_t)(j * CW + 32), rb);
+          if (p.ln_part && j == 0) {
+            // the per-part sums travel from L2 while the first accumulator chunk travels from TMEM: in the epilogue-
+            // bound GELU GEMM there is no idle time before the accumulator wait to hide this latency behind
+            const int row = row0 + r;
+            if (row < p.M) {
+              const float2* pp = reinterpret_cast<const float2*>(p.ln_part) + (size_t)row * p.ln_parts;
+              float2 q2[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)              // all loads in flight at once (ln_parts <= 8)
+                q2[k] = k < p.ln_parts ? __ldg(pp + k) : make_float2(0.f, 0.f);
+              float sm = 0.f, sq = 0.f;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { sm += q2[k].x; sq += q2[k].y; }   // fixed order
+              const float inv_e = 1.0f / (float)p.K;
+              const float dlt = sm * inv_e;                            // mu - mref
+              const float var = fmaxf(fmaf(-dlt, dlt, sq * inv_e), 0.f);
+              lnA = rsqrtf(var + p.ln_eps);
+              lnB = -lnA * dlt;
+              if (t.n_blk == 0 && t.col_off == 0 && half == 0) {        // one writer per row
+                p.ln_mean[row] = (p.ln_mref ? __ldg(p.ln_mref + row) : 0.f) + dlt;
+                p.ln_rstd[row] = lnA;
+              }
+            }
+          }
           const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4);
           if (C::BWD_ACT) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
           if (tlc) TL(TL_CHUNK + 6 * j + 0);
@@ -587,16 +596,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           if (p.ln_part) {
             const float4* b4 = reinterpret_cast<const float4*>(sb + j * CW);
-            const float4* c4 = reinterpret_cast<const float4*>(p.ln_cs + col);
+            const uint2* c2 = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(sbias_all + 256) + half * 128 +
+                                                             j * CW);
             const unsigned long long a2 = f2_pack(lnA, lnA), b2 = f2_pack(lnB, lnB);
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float4 bb = b4[i];
-              const float4 cc = __ldg(c4 + i);
-              f2_unpack(f2_fma(a2, f2_pack(v[4 * i], v[4 * i + 1]), f2_fma(b2, f2_pack(cc.x, cc.y), f2_pack(bb.x, bb.y))),
+              const uint2 cw = c2[i];                              // four bf16 column sums
+              const float2 c01 = unpack_bf16x2(cw.x), c23 = unpack_bf16x2(cw.y);
+              f2_unpack(f2_fma(a2, f2_pack(v[4 * i], v[4 * i + 1]), f2_fma(b2, f2_pack(c01.x, c01.y), f2_pack(bb.x, bb.y))),
                         v[4 * i], v[4 * i + 1]);
               f2_unpack(f2_fma(a2, f2_pack(v[4 * i + 2], v[4 * i + 3]),
-                               f2_fma(b2, f2_pack(cc.z, cc.w), f2_pack(bb.z, bb.w))),
+                               f2_fma(b2, f2_pack(c23.x, c23.y), f2_pack(bb.z, bb.w))),
                         v[4 * i + 2], v[4 * i + 3]);
             }
           } else if (p.bias) {

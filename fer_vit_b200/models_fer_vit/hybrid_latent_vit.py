@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from .. import _lib as L
 from ..native_module import NativeModule, base_config
-from .vit_blocks import create_vit
+from .vit_blocks import check_block_structure, create_vit
 
 
 class AdapterModule(nn.Module):
@@ -113,6 +113,7 @@ class HybridLatentViT(NativeModule):
 
     # ---- native plan description ---------------------------------------------------------------
     def _plan_config(self) -> L.Config:
+        check_block_structure(self.transformer)
         blk0 = self.transformer[0]
         c = base_config()
         c.input_kind, c.L, c.Din, c.E, c.depth = 0, self.seq_len, self.latent_dim, self.embed_dim, len(self.transformer)

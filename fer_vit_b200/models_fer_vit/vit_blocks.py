@@ -26,6 +26,9 @@ def register_vit_config(name: str, embed_dim: int, depth: int, heads: int) -> No
     VIT_CONFIGS[name] = (embed_dim, depth, heads)
 
 
+_WARNED_TORCH_PATH = False
+
+
 class Attention(nn.Module):
     def __init__(self, dim: int, num_heads: int):
         super().__init__()
@@ -65,6 +68,17 @@ class Block(nn.Module):
         self.mlp = Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x):
+        """PyTorch-op evaluation of the block: compatibility surface for callers that invoke `model.transformer(x)`
+        directly (evaluate_model.py:255, an analysis pass). The model's own forward never comes here (it runs the
+        native plan); recording an autograd graph through this path would be a fallback off the CUDA kernels, so it
+        warns (once) instead of staying silent."""
+        global _WARNED_TORCH_PATH
+        if not _WARNED_TORCH_PATH and torch.is_grad_enabled() and (
+                x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            import warnings
+            warnings.warn("fer_vit_b200: Block.forward is a PyTorch-op compatibility path for analysis code; training "
+                          "should go through the model's forward (the native sm_100a plan)", stacklevel=2)
+            _WARNED_TORCH_PATH = True
         x = x + self.attn(self.norm1(x))
         return x + self.mlp(self.norm2(x))
 
@@ -97,9 +111,53 @@ def create_vit(name: str, pretrained: bool):
         import timm  # type: ignore
     except ImportError:
         timm = None
-    if timm is not None and name not in VIT_CONFIGS or (timm is not None and pretrained):
+    if timm is not None and (name not in VIT_CONFIGS or pretrained):
         return timm.create_model(name, pretrained=pretrained, num_classes=0)
     if pretrained:
         raise ImportError("timm is required to load pretrained ViT weights. Install with: pip install timm "
                           "(use_pretrained=False builds the same architecture with random weights)")
     return VisionTransformerShell(name)
+
+
+def check_block_structure(blocks) -> None:
+    """The native plan implements the timm ViT block at create_model defaults: pre-norm LayerNorm,
+    fused qkv Linear WITH bias, no q/k norm, no LayerScale, no DropPath / projection dropout, Mlp = fc1 -> GELU -> fc2.
+    Any other timm variant (deit3 / LayerScale models, qkv_bias=False, qk_norm=True, SwiGLU MLPs ...) would run through
+    the kernels with silently wrong arithmetic, so it is refused here by name."""
+    def is_identity(m):
+        return m is None or isinstance(m, nn.Identity)
+    for i, b in enumerate(blocks):
+        problems = []
+        for name in ("ls1", "ls2", "drop_path1", "drop_path2", "drop_path"):
+            if not is_identity(getattr(b, name, None)):
+                problems.append(f"{name} = {type(getattr(b, name)).__name__}")
+        attn = getattr(b, "attn", None)
+        mlp = getattr(b, "mlp", None)
+        if attn is None or mlp is None or not hasattr(b, "norm1") or not hasattr(b, "norm2"):
+            problems.append("missing norm1 / attn / norm2 / mlp")
+        else:
+            for name in ("q_norm", "k_norm"):
+                if not is_identity(getattr(attn, name, None)):
+                    problems.append(f"attn.{name} = {type(getattr(attn, name)).__name__}")
+            if getattr(attn.qkv, "bias", None) is None or getattr(attn.proj, "bias", None) is None:
+                problems.append("attn.qkv / attn.proj without bias")
+            for name in ("attn_drop", "proj_drop"):
+                d = getattr(attn, name, None)
+                if d is not None and float(getattr(d, "p", 0.0)) > 0.0:
+                    problems.append(f"attn.{name}.p = {d.p}")
+            if not (hasattr(mlp, "fc1") and hasattr(mlp, "fc2")) or getattr(mlp.fc1, "bias", None) is None \
+                    or getattr(mlp.fc2, "bias", None) is None:
+                problems.append("mlp is not fc1 -> act -> fc2 with biases")
+            elif not isinstance(getattr(mlp, "act", nn.GELU()), nn.GELU) or getattr(mlp.act, "approximate", "none") != "none":
+                problems.append(f"mlp.act = {type(mlp.act).__name__} (exact-erf GELU expected)")
+            if not is_identity(getattr(mlp, "norm", None)):
+                problems.append("mlp.norm is not Identity")
+            for name in ("drop1", "drop2", "drop"):
+                d = getattr(mlp, name, None)
+                if d is not None and float(getattr(d, "p", 0.0)) > 0.0:
+                    problems.append(f"mlp.{name}.p = {d.p}")
+            if not isinstance(b.norm1, nn.LayerNorm) or not isinstance(b.norm2, nn.LayerNorm):
+                problems.append("norm1 / norm2 are not nn.LayerNorm")
+        if problems:
+            raise NotImplementedError(f"fer_vit_b200: transformer block {i} is not a default timm ViT block and has no "
+                                      f"native kernel path: {'; '.join(problems)}")

@@ -68,6 +68,12 @@ class NativeModule(nn.Module):
         return self.__dict__["_runner"]
 
     def _native_forward(self, x: torch.Tensor) -> torch.Tensor:
+        # the native launches go to the CURRENT device's stream and the library's per-process caches (SM count, kernel
+        # attributes) belong to it: run under the input's device so that a model on cuda:1 works without the caller
+        # having called torch.cuda.set_device(1), as it would with PyTorch ops
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):
+                return run_plan(self.plan_runner(), self._plan_tensors(), x, self.training)
         return run_plan(self.plan_runner(), self._plan_tensors(), x, self.training)
 
     def __getstate__(self):

@@ -37,6 +37,7 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step_dev: Optional[torch.Tensor] = None
         self._scratch: Optional[torch.Tensor] = None
         self.last_total_norm: Optional[torch.Tensor] = None   # view of the scratch buffer (valid with clipping)
+        self._stepped = False
 
     # ------------------------------------------------------------------ device tables
     def _hyper_rows(self):
@@ -51,6 +52,21 @@ class FusedAdamW(torch.optim.Optimizer):
             return
         self._hyper_dev.copy_(torch.tensor(rows, dtype=torch.float32), non_blocking=False)
         self._hyper_host = rows
+
+    def load_state_dict(self, state_dict) -> None:
+        """torch semantics, plus: the shared device step counter is re-seeded from the loaded state (also when this
+        optimizer has already stepped, e.g. after a GraphedTrainStep warm-up or a resume in the same process)."""
+        super().load_state_dict(state_dict)
+        steps = [float(torch.as_tensor(st["step"]).reshape(-1)[0]) for st in self.state.values() if "step" in st]
+        if steps:
+            if max(steps) != min(steps):
+                raise RuntimeError("fer_vit_b200: FusedAdamW keeps one step counter for all tensors; the loaded state "
+                                   f"holds different steps ({min(steps)} .. {max(steps)})")
+            if self._step_dev is not None:
+                self._step_dev.fill_(steps[0])      # in place: a captured graph keeps reading this tensor
+                for st in self.state.values():
+                    st["step"] = self._step_dev
+        self._stepped = bool(steps) and steps[0] > 0
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -78,6 +94,13 @@ class FusedAdamW(torch.optim.Optimizer):
                 if len(st) != 0 and st.get("step") is not self._step_dev:
                     st["step"] = self._step_dev
                 if len(st) == 0:
+                    if self._step_dev is not None and self._stepped:
+                        # every tensor shares ONE device step counter (that is what makes the step graph-capturable); a
+                        # tensor that joins later would be bias-corrected with the others' t instead of t = 1
+                        raise RuntimeError(
+                            "fer_vit_b200: FusedAdamW saw a parameter without optimizer state after it has already "
+                            "stepped (a parameter was unfrozen or added mid-training). Build a new FusedAdamW over the "
+                            "new trainable set (state_dict() / load_state_dict() carry the moments over)")
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     if self._step_dev is None:
@@ -113,4 +136,5 @@ class FusedAdamW(torch.optim.Optimizer):
                                           C.c_float(self.max_grad_norm),
                                           self._scratch.data_ptr() if self._scratch is not None else None,
                                           torch.cuda.current_stream().cuda_stream))
+        self._stepped = True
         return loss

@@ -94,6 +94,9 @@ class PlanRunner:
     # ------------------------------------------------------------------ binding
     def bind(self, tensors: Dict[int, torch.Tensor]) -> None:
         """(Re)bind parameter pointers and refresh stale bf16 weight-cache entries."""
+        devs = {t.device for t in tensors.values()}
+        if len(devs) > 1:
+            raise RuntimeError(f"fer_vit_b200: the model's parameters live on several devices ({sorted(map(str, devs))})")
         ptrs = [0] * self.nslots
         for s, t in tensors.items():
             ptrs[s] = t.data_ptr()
@@ -139,17 +142,21 @@ class PlanRunner:
     # ------------------------------------------------------------------ LayerNorm folding
     def _update_ln_fold(self, tensors: Dict[int, torch.Tensor]) -> None:
         """Frozen norm + frozen weight behind it => the norm is folded into that GEMM (include/fervit_b200.h:
-        fervit_plan_set_ln_fold). Decided per block from requires_grad; FERVIT_LN_FOLD=0 switches it off."""
+        fervit_plan_set_ln_fold). Decided per block from requires_grad; FERVIT_LN_FOLD=0 switches it off (1 / 2: norm1 /
+        norm2 only)."""
         d = self.depth
         f1, f2 = [0] * d, [0] * d
         cfg = self.cfg
-        on = os.environ.get("FERVIT_LN_FOLD", "1") != "0"
-        if on and cfg.norm_first and cfg.E % 128 == 0 and cfg.E <= 1024:
+        try:   # bit 0: norm1 -> qkv, bit 1: norm2 -> fc1 (A/B runs); default both
+            mask = int(os.environ.get("FERVIT_LN_FOLD", "3"))
+        except ValueError:
+            mask = 3
+        if mask and cfg.norm_first and cfg.E % 128 == 0 and cfg.E <= 1024:
             def frozen(blk, names):
                 return all((L.bslot(blk, n) in tensors) and not tensors[L.bslot(blk, n)].requires_grad for n in names)
             for i in range(d):
-                f1[i] = int(i > 0 and frozen(i, (L.B_LN1_W, L.B_LN1_B, L.B_QKV_W, L.B_QKV_B)))
-                f2[i] = int(frozen(i, (L.B_LN2_W, L.B_LN2_B, L.B_FC1_W, L.B_FC1_B)))
+                f1[i] = int(bool(mask & 1) and i > 0 and frozen(i, (L.B_LN1_W, L.B_LN1_B, L.B_QKV_W, L.B_QKV_B)))
+                f2[i] = int(bool(mask & 2) and frozen(i, (L.B_LN2_W, L.B_LN2_B, L.B_FC1_W, L.B_FC1_B)))
         key = (tuple(f1), tuple(f2))
         if key != getattr(self, "_fold_key", None):
             L.check(self._lib.fervit_plan_set_ln_fold(self._h, (C.c_int * d)(*f1), (C.c_int * d)(*f2), d))
@@ -193,6 +200,8 @@ class PlanRunner:
     # ------------------------------------------------------------------ forward / backward
     def forward(self, x: torch.Tensor, training: bool, save: bool):
         _require_cuda(x, "the input")
+        if self._wcache is not None and self._wcache.device != x.device:
+            raise RuntimeError(f"fer_vit_b200: the input is on {x.device} but the model is on {self._wcache.device}")
         if x.dtype != torch.float32:
             raise RuntimeError(f"fer_vit_b200: input must be float32 (got {x.dtype})")
         x = x.contiguous()
@@ -292,6 +301,8 @@ class _PlanFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         x, *tensors = ctx.saved_tensors
+        if x.device.index != torch.cuda.current_device():   # autograd's thread: same device as the forward
+            torch.cuda.set_device(x.device)
         ctx.runner.bind(dict(zip(ctx.slots, tensors)))   # another forward may have re-bound the plan since
         if ctx.needs_input_grad[4]:
             raise NotImplementedError("fer_vit_b200: gradient with respect to the model input is not implemented "

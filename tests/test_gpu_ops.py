@@ -430,6 +430,44 @@ def test_fused_adamw_matches_torch(lib, max_norm):
     assert max(errs) < 2e-6, errs
 
 
+def test_fused_adamw_step_counter_rules(lib):
+    """One shared device step counter: a parameter that joins after the optimizer has stepped is refused
+    (it would be bias-corrected with t instead of 1), and load_state_dict() into an optimizer that has ALREADY stepped
+    re-seeds the counter from the loaded state, so the next update is step t+1 of the loaded run, as in torch."""
+    import fer_vit_b200 as fv
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mk = lambda: [torch.nn.Parameter(torch.randn(33, 17, device="cuda", generator=g)) for _ in range(2)]
+    ref, our = mk(), None
+    our = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.AdamW(ref, lr=1e-2, weight_decay=0.01)
+    o_our = fv.FusedAdamW(our, lr=1e-2, weight_decay=0.01)
+    grads = [[torch.randn(33, 17, device="cuda", generator=g) for _ in range(2)] for _ in range(5)]
+
+    def run(o, ps, k):
+        for p_, gr in zip(ps, grads[k]):
+            p_.grad = gr.clone()
+        o.step()
+    for k in range(3):
+        run(o_ref, ref, k); run(o_our, our, k)
+    import copy
+    sd = copy.deepcopy(o_our.state_dict())     # a snapshot (state_dict() itself returns references, as in torch)
+    run(o_our, our, 3)                         # the optimizer moves on (counter = 4) ...
+    with torch.no_grad():                      # ... then is rolled back to the saved run
+        for a, b in zip(ref, our):
+            b.copy_(a)
+    o_our.load_state_dict(sd)                  # moments and step = 3 restored into the SAME optimizer object
+    run(o_ref, ref, 3); run(o_our, our, 3)
+    assert max(relerr(b, a) for a, b in zip(ref, our)) < 2e-6
+    # late joiner
+    late = torch.nn.Parameter(torch.randn(5, device="cuda", generator=g))
+    o_our.add_param_group({"params": [late]})
+    for p_ in our:
+        p_.grad = torch.zeros_like(p_)
+    late.grad = torch.ones_like(late)
+    with pytest.raises(RuntimeError, match="without optimizer state"):
+        o_our.step()
+
+
 # ------------------------------------------------------------------------------------------------ fused adapter
 @pytest.mark.parametrize("T,E", [(128, 256), (300, 768), (4864, 768), (19 * 7, 512)])
 def test_adapter_fused_tcgen05(lib, T, E):

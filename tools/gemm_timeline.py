@@ -47,7 +47,7 @@ def shapes(M):
     }
 
 
-def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd=False, iters=5):
+def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd=False, iters=5, bn=0):
     x = torch.randn(M, K, device="cuda").bfloat16()
     W = torch.randn(N, K, device="cuda").bfloat16()
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
@@ -64,10 +64,10 @@ def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd
         if mul_bwd:
             # dX = dY W (transposed weight [K_in = N here]) with the saved derivative multiplied in
             L.check(lib.fervit_linear_dgrad(L.BF16, x.data_ptr(), W.data_ptr(), p(aux), None, M, K, N, 3,
-                                            out.data_ptr(), None, 0, st))   # reduction over K (API name: N)
+                                            out.data_ptr(), None, bn, st))   # reduction over K (API name: N)
         else:
             L.check(lib.fervit_linear_forward(L.BF16, x.data_ptr(), W.data_ptr(), p(b), p(r), M, N, K, act,
-                                              None if out_f32 else out.data_ptr(), p(of), p(pre), 0, st))
+                                              None if out_f32 else out.data_ptr(), p(of), p(pre), bn, st))
     ev = []
     for _ in range(iters):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -87,19 +87,20 @@ def run(name, M, N, K, bias=False, residual=False, out_f32=False, act=0, mul_bwd
             if t[s] >= t[0] and t[s] != 0 and t[s] <= t[20] + 10:
                 rec[nm] = round((t[s] - t[0]) / ghz / 1e3, 2)
         rows.append(rec)
-    return {"gemm": name, "M": M, "N": N, "K": K, "event_us_median": round(sorted(ev)[len(ev) // 2], 1), "ctas": rows}
+    return {"gemm": name, "M": M, "N": N, "K": K, "bn": bn, "event_us_median": round(sorted(ev)[len(ev) // 2], 1), "ctas": rows}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--shapes", default="qkv,proj,fc1,fc2,fc2_dgrad,fc1_dgrad")
     ap.add_argument("--m", type=int, default=4864)
+    ap.add_argument("--bn", type=int, default=0, help="force the N tile of the CTA-pair kernel (128 / 256)")
     a = ap.parse_args()
     sh = shapes(a.m)
     for name in a.shapes.split(","):
         kw = dict(sh[name])
         N, K = kw.pop("N"), kw.pop("K")
-        print(json.dumps(run(name, a.m, N, K, **kw)), flush=True)
+        print(json.dumps(run(name, a.m, N, K, bn=a.bn, **kw)), flush=True)
 
 
 if __name__ == "__main__":
