@@ -85,11 +85,30 @@ class GraphedTrainStep:
         if self.graph is None:
             raise RuntimeError("fer_vit_b200: this graphed train step has been closed")
 
+    def _host_launched(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        """The same step with every kernel launched from the host (same native kernels, no graph): the path of a
+        batch whose shape differs from the captured one, e.g. the last, partial batch of an epoch
+        (DataLoader(drop_last=False), train_hybrid_latent_vit.py:212-217)."""
+        self._seed_dev.add_(1)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_fn(self.model(x), y)
+        loss.backward()
+        self.optimizer.step()
+        # the captured graph addresses the gradient tensors of ITS replays: drop the ones just produced so the next
+        # replay does not see stale .grad objects of another shape's backward
+        self.optimizer.zero_grad(set_to_none=True)
+        return loss.detach()
+
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self._check_open()
-        if x.shape != self.static_x.shape or y.shape != self.static_y.shape:
-            raise RuntimeError(f"fer_vit_b200: GraphedTrainStep was captured for {tuple(self.static_x.shape)} / "
+        if x.shape[1:] != self.static_x.shape[1:] or x.dtype != self.static_x.dtype or y.dim() != self.static_y.dim():
+            raise RuntimeError(f"fer_vit_b200: GraphedTrainStep was captured for inputs {tuple(self.static_x.shape)} / "
                                f"{tuple(self.static_y.shape)}, got {tuple(x.shape)} / {tuple(y.shape)}")
+        if x.shape[0] != self.static_x.shape[0]:
+            if x.shape[0] != y.shape[0] or x.shape[0] == 0:
+                raise RuntimeError("fer_vit_b200: GraphedTrainStep: inputs and labels must hold the same, non-zero "
+                                   "number of samples")
+            return self._host_launched(x, y)      # another batch size: same kernels, launched from the host
         self.static_x.copy_(x, non_blocking=True)
         self.static_y.copy_(y, non_blocking=True)
         self.graph.replay()

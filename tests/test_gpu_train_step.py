@@ -200,3 +200,42 @@ def test_per_parameter_requires_grad_inside_blocks(precision):
     worst = max(errs, key=errs.get)
     record("per_parameter_requires_grad", precision=precision, worst_grad=errs[worst], worst_key=worst)
     assert errs[worst] < tol, (worst, errs[worst])
+
+
+def test_graphed_step_takes_a_partial_last_batch():
+    """A batch of another size than the captured one (the last batch of an epoch with drop_last=False) runs the same
+    step host-launched instead of being refused; graph replays before and after it still work, and the whole sequence
+    equals the eager loop bit for bit."""
+    import copy
+    import fer_vit_b200 as fv
+    g = load_golden("hybrid_adapter")
+    gen = torch.Generator().manual_seed(3)
+    xs = [torch.randn(b, 18, 64, generator=gen).cuda() for b in (8, 8, 5, 8)]
+    ys = [torch.randint(0, 7, (x.shape[0],), generator=gen).cuda() for x in xs]
+
+    def make():
+        m = build_model("hybrid_adapter", "bf16")
+        m.load_state_dict(g["sd"], strict=True)
+        m = m.cuda().eval()                      # eval: no head-dropout draws, so both loops are deterministic
+        o = fv.FusedAdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.01)
+        return m, o
+    m1, o1 = make()
+    stepper = fv.GraphedTrainStep(m1, o1, xs[0], ys[0], warmup=1)
+    sd0 = copy.deepcopy(m1.state_dict())
+    m2, o2 = make()
+    m2.load_state_dict(sd0)
+    o2.load_state_dict(copy.deepcopy(o1.state_dict()))
+    l1 = [float(stepper(x, y)) for x, y in zip(xs, ys)]
+    l2 = []
+    for x, y in zip(xs, ys):
+        o2.zero_grad(set_to_none=True)
+        loss = fv.cross_entropy(m2(x), y)
+        loss.backward()
+        o2.step()
+        l2.append(float(loss))
+    assert l1 == l2, (l1, l2)
+    for (k, a), (_, b) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    with pytest.raises(RuntimeError, match="captured for inputs"):
+        stepper(torch.randn(8, 17, 64, device="cuda"), ys[0])
+    stepper.close()
