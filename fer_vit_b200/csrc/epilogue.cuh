@@ -34,6 +34,13 @@ static inline int epilogue_kind(const Epilogue& e) {
   return EPK_PLAIN;
 }
 
+// the kind `e` would have without its dropout (the CTA-pair kernel carries dropout as a separate template flag)
+static inline int epilogue_kind_nodrop(const Epilogue& e) {
+  Epilogue q = e;
+  q.drop.threshold = 0;
+  return epilogue_kind(q);
+}
+
 // Apply the epilogue to NV consecutive columns [col, col+NV) of logical row `row`.
 // Caller guarantees row < M and col + NV <= N, NV % 4 == 0 and col % 4 == 0.
 // pre_aux / pre_res: side inputs the caller already fetched (software-pipelined epilogues, NV == 4); nullptr = load here.

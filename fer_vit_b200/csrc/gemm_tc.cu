@@ -490,8 +490,9 @@ int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool
   const int kind = epilogue_kind(epi);
   // forward / dgrad shapes go to the CTA-pair kernel (gemm_tc2.cu); this single-CTA kernel keeps the MN-major
   // (wgrad), split-K, row-remapping and dropout epilogues
-  if (!a_mn && !b_mn && p.splits == 1 && force_bn >= 0 && gemm_bf16_tc2_supported(M, N, K, lda, ldb, epi, kind))
-    return gemm_bf16_tc2(A, lda, B, ldb, M, N, K, force_bn, epi, kind, stream);
+  const int kind2 = epilogue_kind_nodrop(epi);   // the CTA-pair kernel takes dropout as a flag beside the kind
+  if (!a_mn && !b_mn && p.splits == 1 && force_bn >= 0 && gemm_bf16_tc2_supported(M, N, K, lda, ldb, epi, kind2))
+    return gemm_bf16_tc2(A, lda, B, ldb, M, N, K, force_bn, epi, kind2, stream);
   FV_CHECK(!epi.ln_part && !epi.lnp_part, "gemm_bf16_tc: a folded LayerNorm needs the CTA-pair kernel, which does not "
            "support this problem (M=%d N=%d K=%d)", M, N, K);
   if (force_bn < 0) force_bn = -force_bn;  // negative: force this kernel with that tile width (benchmarks)

@@ -106,7 +106,7 @@ enum { TL_ENTRY = 0, TL_PROLOGUE = 1, TL_GRIDSYNC = 2, TL_FIRST_FULL = 3, TL_MMA
        // 3 staging tile free (earlier stores have read it), 4 staged + fenced, 5 stores issued}
        TL_CHUNK = 32 };
 
-template <int BN, int KIND, int F32, bool SK>
+template <int BN, int KIND, int F32, bool SK, bool DROP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                 const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_z,
@@ -275,6 +275,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     const uint32_t tmem_empty0[2] = {mapa(smem_u32(&tmem_empty[0]), 0), mapa(smem_u32(&tmem_empty[1]), 0)};
     float alpha = p.alpha;
     if (p.alpha_ptr) alpha *= __ldg(p.alpha_ptr);
+    const uint64_t dseed = DROP ? p.drop.eff() : 0;   // host seed + the device counter a captured graph bumps
     const int r = lane;
     uint32_t g = 0;  // chunks processed so far: double-buffered tiles use g & 1, load-barrier parity = (g >> 1) & 1
     Item w;
@@ -445,6 +446,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (alpha != 1.0f) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] *= alpha;
+          }
+          if constexpr (DROP) {   // dropout1 / dropout2 of the post-norm layer: on the sub-layer output, before the residual
+            const uint64_t base = (uint64_t)(row0 + r) * (uint64_t)p.N + (uint64_t)col;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              v[i] = drop_keep(dseed, p.drop.site, base + i, p.drop.threshold) ? v[i] * p.drop.scale : 0.0f;
           }
           // the bf16 tile [yb] was last the source of chunk g-2's stores (and, without a residual, the fp32 tile too)
           if (tlc) TL(TL_CHUNK + 6 * j + 2);
@@ -694,6 +701,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               }
             }
           }
+          if constexpr (DROP) {   // on the activated (or derivative-scaled) value; the saved act' tile is not masked
+            const uint64_t base = (uint64_t)(row0 + r) * (uint64_t)p.N + (uint64_t)col;
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              v[i] = drop_keep(dseed, p.drop.site, base + i, p.drop.threshold) ? v[i] * p.drop.scale : 0.0f;
+          }
           if (p.has_out) {
             uint8_t* yrow = Ys + r * 128;
 #pragma unroll
@@ -888,12 +901,19 @@ static int launch(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
   if (p.has_f32) FV_TRY(make_tmap_2d(&tx, e.out_f32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
   if (p.has_res) FV_TRY(make_tmap_2d(&tr, e.residual, 4, (uint64_t)N, (uint64_t)M, (uint64_t)e.ldo, CHUNK, 32, 128));
   constexpr bool CAN_SK = (KIND == EPK_PLAIN);
-  auto kernel = gemm_tc2_kernel<BN, KIND, F32, false>;
-  if (CAN_SK && p.sk_q) kernel = gemm_tc2_kernel<BN, KIND, F32, CAN_SK>;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[p.sk_q ? 1 : 0]) {
+  // dropout epilogues exist for the forward kinds and the saved-derivative backward (what the post-norm layers use)
+  constexpr bool CAN_DROP = (KIND == EPK_PLAIN || KIND == EPK_GELU || KIND == EPK_RELU || KIND == EPK_MUL_BWD);
+  p.drop = e.drop;
+  FV_CHECK(!e.drop.threshold || CAN_DROP, "gemm_bf16_tc2: no dropout epilogue for kind %d", KIND);
+  if (e.drop.threshold) { p.sk_q = 0; p.sk_tiles = 0; }
+  auto kernel = gemm_tc2_kernel<BN, KIND, F32, false, false>;
+  if (CAN_SK && p.sk_q) kernel = gemm_tc2_kernel<BN, KIND, F32, CAN_SK, false>;
+  if (CAN_DROP && e.drop.threshold) kernel = gemm_tc2_kernel<BN, KIND, F32, false, CAN_DROP>;
+  const int variant = e.drop.threshold ? 2 : (p.sk_q ? 1 : 0);
+  static bool attr_set[3] = {false, false, false};
+  if (!attr_set[variant]) {
     FV_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set[p.sk_q ? 1 : 0] = true;
+    attr_set[variant] = true;
   }
   const int units = p.virt_units;
   const int max_pairs = num_sms() / 2;
@@ -995,6 +1015,10 @@ int gemm_tc2_timeline(unsigned long long* out, int n) {
 // Can the CTA-pair kernel run this problem? (K-major operands, no split-K, plain / activation epilogues.)
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind) {
   (void)M;
+  if (e.drop.threshold) {   // `kind` is the kind WITHOUT the dropout (epilogue_kind_nodrop)
+    if (kind != EPK_PLAIN && kind != EPK_GELU && kind != EPK_RELU && kind != EPK_MUL_BWD) return false;
+    if (e.remap_L > 0) return false;
+  }
   if (kind != EPK_PLAIN && kind != EPK_GELU && kind != EPK_RELU && kind != EPK_GELU_BWD && kind != EPK_RELU_BWD &&
       kind != EPK_MUL_BWD)
     return false;

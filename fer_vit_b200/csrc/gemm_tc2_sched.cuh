@@ -4,6 +4,7 @@
 // owner's expected partial count) are checked on the CPU by tests/host/streamk_sched_host.cu.
 #pragma once
 #include <cstddef>
+#include "common.cuh"   // Dropout
 
 namespace fervit {
 namespace tc2 {
@@ -46,6 +47,9 @@ struct Params {
   const float* ln_part; const float* ln_mref; const float* ln_cs; float* ln_mean; float* ln_rstd;
   float ln_eps; int ln_parts;
   float* lnp_part; const float* lnp_mref;
+  // counter-based dropout on the epilogue's value, before the residual add (nn.TransformerEncoderLayer's dropout1 /
+  // dropout / dropout2 of the post-norm models); threshold 0 = off. Kernels are instantiated with and without it.
+  Dropout drop;
 };
 
 
