@@ -90,6 +90,7 @@ SIGNATURES = {
     "fervit_set_gemm_scratch": (_i, [_p, _ll]),
     "fervit_debug_gemm_clock": (_i, [_p, _p]),
     "fervit_debug_gemm_timeline": (_i, [_p, _i]),
+    "fervit_debug_adapter_timeline": (_i, [_p, _i]),
     "fervit_gemm_prof": (_i, [_i, _p]),
     "fervit_gemm_prof_read": (_i, [_p, _p, _p, _p, _i]),
     "fervit_adapter_forward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p]),

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace fervit {
 namespace adp {
@@ -42,7 +43,11 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + BW_BYTES + BAR_BYTES
 constexpr int TMEM_COLS = 512;           // H at columns [0, 64), Y at [256, 512)
 static_assert(SMEM_BYTES <= 232448, "adapter kernel: shared memory");
 
+// FERVIT_GEMM_DEBUG bit 64: clock64 stamps of CTA 0 at its phase boundaries (tools/gemm_timeline.py --adapter)
+__device__ unsigned long long g_adapter_timeline[32];
+
 struct Params {
+  int debug;
   int T, E, groups;        // rows, width, column groups (E / 256)
   int backward;            // 0: forward (f = GELU + b1), 1: backward (f = alpha * h * d)
   const float* b1;         // [64]   forward
@@ -84,7 +89,17 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   const int row_blk = blockIdx.x / p.groups, cg = blockIdx.x % p.groups;
   const int total_kb = (p.E + BK - 1) / BK;
 
+  const bool tl_on = (p.debug & 64) && blockIdx.x == 0;
+  auto TL = [&](int slot) {
+    if (tl_on) g_adapter_timeline[slot] = (unsigned long long)clock64();
+  };
   pdl_trigger();
+  if (tl_on && threadIdx.x == 0) {
+    TL(0);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_adapter_timeline[30] = t;
+  }
   if (warp == W_TMA && lane == 0) {
     prefetch_tmap(&tm_in); prefetch_tmap(&tm_aw); prefetch_tmap(&tm_bw);
     prefetch_tmap(&tm_res); prefetch_tmap(&tm_out);
@@ -107,7 +122,9 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) TL(1);
   pdl_grid_sync();
+  if (threadIdx.x == 0) TL(2);
 
   if (warp == W_TMA) {
     if (lane == 0) {
@@ -132,6 +149,7 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int kb = 0; kb < total_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase, 12);
         tc_fence_after();
+        if (kb == 0) TL(3);
         const uint32_t a_addr = smem_u32(smem_in + stage * IN_BYTES);
         const uint32_t b_addr = smem_u32(smem_aw + stage * AW_BYTES);
 #pragma unroll
@@ -142,6 +160,7 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       umma_commit(h_full);
+      TL(4);
       // phase 3: the epilogue warps have written G (generic proxy -> fenced), the B tile has landed
       mbar_wait(g_ready, 0, 13);
       mbar_wait(b_full, 0, 14);
@@ -152,6 +171,7 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         umma_bf16<1>(tmem_base + 256u, make_smem_desc(g_addr + k * (UMMA_K * 2), 16, 1024),
                      make_smem_desc(w_addr + k * (UMMA_K * 2), 16, 1024), idesc2, k > 0 ? 1u : 0u);
       umma_commit(y_full);
+      TL(7);
     }
   } else if (warp < EPI_WARPS) {
     const int quarter = warp & 3, half = warp >> 2;
@@ -173,6 +193,7 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // ---------------- phase 2: G = f(H) ----------------
     mbar_wait(h_full, 0, 15);
     tc_fence_after();
+    if (warp == 0 && lane == 0) TL(5);
     // the ring is free now (all phase-1 MMAs have completed): the residual tiles travel during phases 2-3
     if (lane == 0 && rows_live) { issue_res(0); issue_res(1); }
     {
@@ -230,10 +251,12 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(g_ready);
+    if (warp == 0 && lane == 0) TL(6);
 
     // ---------------- phase 4: out = res + alpha * (Y + b2) ----------------
     mbar_wait(y_full, 0, 16);
     tc_fence_after();
+    if (warp == 0 && lane == 0) TL(8);
     if (rows_live) {
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + 256u + (uint32_t)(half * (NC / 2));
       const uint32_t xsw = (uint32_t)(r & 7), ysw = (uint32_t)((r >> 1) & 3);
@@ -300,8 +323,10 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
             issue_res(j + 2);
           }
         }
+        if (warp == 0 && lane == 0) TL(10 + j);
       }
       if (lane == 0) tma_store_wait_read<0>();
+      if (warp == 0 && lane == 0) TL(14);
       if (p.lnp_part && row < p.T)
         reinterpret_cast<float2*>(p.lnp_part)[(size_t)row * (p.E >> 7) + (col_base >> 7)] = make_float2(ln_s1, ln_s2);
     }
@@ -311,9 +336,22 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   if (warp == W_ALLOC) tmem_dealloc<1>(tmem_base, (uint32_t)TMEM_COLS);
+  if (tl_on && threadIdx.x == 0) {
+    TL(15);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_adapter_timeline[31] = t;
+  }
 }
 
 }  // namespace adp
+
+// diagnostics: the phase stamps of CTA 0 of the last adapter launch (32 values; slots in tools/gemm_timeline.py)
+int adapter_timeline(unsigned long long* out, int n) {
+  FV_CHECK(n >= 32, "adapter timeline: need room for 32 values");
+  FV_CUDA(cudaMemcpyFromSymbol(out, adp::g_adapter_timeline, sizeof(unsigned long long) * 32));
+  return 0;
+}
 
 bool adapter_fused_supported(int T, int E, int A) {
   static int off = -1;
@@ -341,6 +379,11 @@ int adapter_fused(int backward, const bf16* in, const bf16* Aw, const bf16* Bw, 
   t_outb = t_in;
   if (out_bf16) FV_TRY(make_tmap_2d(&t_outb, out_bf16, 2, (uint64_t)E, (uint64_t)T, (uint64_t)E, 32, 32, 64));
   adp::Params p;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("FERVIT_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.T = T; p.E = E; p.groups = E / adp::NC; p.backward = backward;
   p.b1 = b1; p.b2 = b2; p.alpha_ptr = alpha_ptr; p.d_in = d_in; p.s0 = s0; p.s1 = s1;
   p.has_out_bf16 = out_bf16 != nullptr;

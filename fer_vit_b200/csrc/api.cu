@@ -158,6 +158,10 @@ FV_API int fervit_debug_gemm_timeline(unsigned long long* out, int n) {
   FV_CHECK(out, "debug_gemm_timeline: null argument");
   return gemm_tc2_timeline(out, n);
 }
+FV_API int fervit_debug_adapter_timeline(unsigned long long* out, int n) {
+  FV_CHECK(out, "debug_adapter_timeline: null argument");
+  return adapter_timeline(out, n);
+}
 
 FV_API int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const void* aux, const float* residual,
                                int M, int N, int K, int act, void* out, float* out_f32, int force_bn, void* stream) {

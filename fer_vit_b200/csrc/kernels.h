@@ -15,6 +15,7 @@ int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, 
                   int kind, cudaStream_t stream);
 int gemm_tc2_clock_probe(double* ns, double* cycles);
 int gemm_tc2_timeline(unsigned long long* out, int n);
+int adapter_timeline(unsigned long long* out, int n);
 int gemm_tc2_prof(int op, cudaStream_t stream);
 int gemm_tc2_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap);
 size_t gemm_tc2_scratch_bytes();

@@ -366,6 +366,8 @@ int fervit_gemm_prof_read(double* us, double* flops, long long* launches, double
 /* Diagnostics: with FERVIT_GEMM_DEBUG bit 64 set, the CTA-pair GEMM stamps clock64 at every phase boundary of two CTAs
  * (row 0: CTA 0, row 1: leader of the last pair); out receives 2 x 64 values (slot meanings: csrc/gemm_tc2.cu TL_*). */
 int fervit_debug_gemm_timeline(unsigned long long* out, int n);
+/* same for the fused AdapterModule kernel (CTA 0, 32 values) */
+int fervit_debug_adapter_timeline(unsigned long long* out, int n);
 
 /* fp32 -> bf16 cast (n multiple of 4) */
 int fervit_cast_bf16(const float* src, void* dst, long long n, void* stream);

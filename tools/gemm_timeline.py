@@ -103,5 +103,57 @@ def main():
         print(json.dumps(run(name, a.m, N, K, bn=a.bn, **kw)), flush=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--adapter" not in sys.argv:
     main()
+
+
+def adapter_timeline(T=4864, E=768):
+    """Phase stamps of CTA 0 of the fused AdapterModule kernel, forward and backward-input."""
+    names = {0: "entry", 1: "prologue done", 2: "grid dependency", 3: "first operands landed",
+             4: "phase 1 MMAs issued", 5: "H ready (warp 0)", 6: "G written (warp 0)", 7: "phase 3 MMAs issued",
+             8: "Y ready (warp 0)", 10: "chunk 0 done", 11: "chunk 1 done", 12: "chunk 2 done", 13: "chunk 3 done",
+             14: "stores drained", 15: "end"}
+    lib = L.lib()
+    x = torch.randn(T, E, device="cuda")
+    xb = x.bfloat16()
+    W1 = (torch.randn(64, E, device="cuda") / E ** 0.5).bfloat16()
+    W2 = (torch.randn(E, 64, device="cuda") / 8).bfloat16()
+    b1, b2 = torch.randn(64, device="cuda"), torch.randn(E, device="cuda")
+    alpha = torch.tensor([0.3], device="cuda")
+    g = torch.empty(T, 64, device="cuda", dtype=torch.bfloat16)
+    d = torch.empty_like(g)
+    y = torch.empty(T, E, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    out = []
+    for which in ("forward", "backward"):
+        ev = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if which == "forward":
+                L.check(lib.fervit_adapter_forward(xb.data_ptr(), x.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
+                                                   b2.data_ptr(), alpha.data_ptr(), T, E, g.data_ptr(), d.data_ptr(),
+                                                   y.data_ptr(), st))
+            else:
+                L.check(lib.fervit_adapter_backward_input(xb.data_ptr(), x.data_ptr(), W2.t().contiguous().data_ptr(),
+                                                          W1.t().contiguous().data_ptr(), alpha.data_ptr(), d.data_ptr(),
+                                                          T, E, g.data_ptr(), y.data_ptr(), xb.data_ptr(), st))
+            e1.record()
+            torch.cuda.synchronize()
+            ev.append(e0.elapsed_time(e1) * 1e3)
+        buf = (ctypes.c_ulonglong * 32)()
+        L.check(lib.fervit_debug_adapter_timeline(buf, 32))
+        t = list(buf)
+        ghz = (t[15] - t[0]) / max(t[31] - t[30], 1)
+        rec = {"kernel": "adapter " + which, "event_us_median": round(sorted(ev)[2], 1),
+               "kernel_us": round((t[31] - t[30]) / 1e3, 2), "sm_ghz": round(ghz, 3)}
+        for s_, nm in sorted(names.items()):
+            if t[s_] >= t[0] and t[s_] <= t[15] + 10:
+                rec[nm] = round((t[s_] - t[0]) / ghz / 1e3, 2)
+        out.append(rec)
+    return out
+
+
+if "--adapter" in sys.argv:
+    for r in adapter_timeline():
+        print(json.dumps(r), flush=True)
