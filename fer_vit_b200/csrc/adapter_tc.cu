@@ -39,7 +39,10 @@ constexpr int BAR_BYTES = 512;
 // The epilogue staging tiles ALIAS the input half of the phase-1 ring: every ring stage is free once the phase-1
 // accumulator is complete (h_full), which is when the residual tiles start to travel.
 static_assert(EPI_WARPS * WARP_STAGING <= STAGES * IN_BYTES, "staging must fit in the aliased ring region");
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + BW_BYTES + BAR_BYTES + 1024;
+// b1 [64] and this column group's b2 [256] staged once by the (otherwise idle) epilogue warps during phase 1: phase 2
+// and every phase-4 chunk paid one global-load latency for them (2.8 us of phase 2, profiles/r02_adapter_timeline.jsonl)
+constexpr int BIAS_BYTES = (AD + NC) * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G_BYTES + BW_BYTES + BAR_BYTES + BIAS_BYTES + 1024;
 constexpr int TMEM_COLS = 512;           // H at columns [0, 64), Y at [256, 512)
 static_assert(SMEM_BYTES <= 232448, "adapter kernel: shared memory");
 
@@ -84,6 +87,8 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   uint64_t* b_full = h_full + 3;             // B tile landed
   uint64_t* ld_bar = h_full + 4;             // [EPI_WARPS][2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(ld_bar + 2 * EPI_WARPS);
+  float* sb1 = reinterpret_cast<float*>(smem_bw + BW_BYTES + BAR_BYTES);   // [64]
+  float* sb2 = sb1 + AD;                                                   // [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row_blk = blockIdx.x / p.groups, cg = blockIdx.x % p.groups;
@@ -190,6 +195,18 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       mbar_expect_tx(&my_ld[j & 1], XT);
       tma_load_2d(Xs + (j & 1) * XT, &tm_res, &my_ld[j & 1], col_base + j * 32, row0);
     };
+    uint4 dv[4];
+    if (!p.backward) {
+      const int t = threadIdx.x;   // 0 .. 255 (the epilogue warps), while the ring feeds phase 1
+      if (t < AD) sb1[t] = __ldg(p.b1 + t);
+      sb2[t] = __ldg(p.b2 + cg * NC + t);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+    } else {
+      // the saved GELU'(u) of this thread's row travels while phase 1 runs
+      const uint4* dp = reinterpret_cast<const uint4*>(p.d_in + (size_t)row * AD + half * 32);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dv[c] = row < p.T ? __ldg(dp + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
     // ---------------- phase 2: G = f(H) ----------------
     mbar_wait(h_full, 0, 15);
     tc_fence_after();
@@ -199,12 +216,6 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     {
       uint32_t hr[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 32), hr);
-      uint4 dv[4];
-      if (p.backward) {
-        const uint4* dp = reinterpret_cast<const uint4*>(p.d_in + (size_t)row * AD + half * 32);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dv[c] = row < p.T ? __ldg(dp + c) : make_uint4(0u, 0u, 0u, 0u);
-      }
       tmem_ld_wait();
       float v[32];
 #pragma unroll
@@ -216,9 +227,8 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       if (!p.backward) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float g0, d0, g1, d1;
-          gelu_fwd_deriv_poly(v[i] + __ldg(p.b1 + half * 32 + i), g0, d0);
-          gelu_fwd_deriv_poly(v[i + 1] + __ldg(p.b1 + half * 32 + i + 1), g1, d1);
+          float g0 = v[i] + sb1[half * 32 + i], g1 = v[i + 1] + sb1[half * 32 + i + 1], d0, d1;
+          gelu_fwd_deriv_poly2(g0, g1, d0, d1);      // packed fp32 (FFMA2), as in the GEMM epilogues
           gq[i >> 1] = pack_bf16x2(g0, g1);
           dq[i >> 1] = pack_bf16x2(d0, d1);
         }
@@ -236,21 +246,25 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int c = 0; c < 4; ++c)
         *reinterpret_cast<uint4*>(grow + (((half * 4 + c) ^ (rloc & 7)) << 4)) =
             make_uint4(gq[4 * c], gq[4 * c + 1], gq[4 * c + 2], gq[4 * c + 3]);
-      if (cg == 0 && row < p.T) {   // one column group keeps the [T, 64] tensors for the backward pass / the wgrads
+      fence_proxy_async_smem();   // generic-proxy writes of G -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_ready);
+      // The [T, 64] tensors the backward pass / the weight gradients need are written AFTER phase 3 has been released
+      // (they sat in front of the arrive: 0.6 us of every row block's critical path) and by two different column
+      // groups, so that no single CTA of a row block carries both.
+      const int cg_d = p.groups > 1 ? 1 : 0;
+      if (cg == 0 && row < p.T) {
         uint4* s0 = reinterpret_cast<uint4*>(p.s0 + (size_t)row * AD + half * 32);
 #pragma unroll
         for (int c = 0; c < 4; ++c) s0[c] = make_uint4(gq[4 * c], gq[4 * c + 1], gq[4 * c + 2], gq[4 * c + 3]);
-        if (!p.backward) {
-          uint4* s1 = reinterpret_cast<uint4*>(p.s1 + (size_t)row * AD + half * 32);
+      }
+      if (!p.backward && cg == cg_d && row < p.T) {
+        uint4* s1 = reinterpret_cast<uint4*>(p.s1 + (size_t)row * AD + half * 32);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) s1[c] = make_uint4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
-        }
+        for (int c = 0; c < 4; ++c) s1[c] = make_uint4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
       }
     }
-    fence_proxy_async_smem();   // generic-proxy writes of G -> visible to the tensor core's async-proxy reads
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(g_ready);
     if (warp == 0 && lane == 0) TL(6);
 
     // ---------------- phase 4: out = res + alpha * (Y + b2) ----------------
@@ -278,10 +292,10 @@ adapter_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         }
         if (j + 1 < 4) tmem_ld32(taddr0 + (uint32_t)((j + 1) * 32), rr);
         if (!p.backward) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col);
+          const float4* b4 = reinterpret_cast<const float4*>(sb2 + half * (NC / 2) + j * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 bb = __ldg(b4 + i);
+            const float4 bb = b4[i];
             v[4 * i] = alpha * (v[4 * i] + bb.x); v[4 * i + 1] = alpha * (v[4 * i + 1] + bb.y);
             v[4 * i + 2] = alpha * (v[4 * i + 2] + bb.z); v[4 * i + 3] = alpha * (v[4 * i + 3] + bb.w);
           }

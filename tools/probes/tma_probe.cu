@@ -11,6 +11,7 @@
 //   mode 2  cluster 4: four CTAs share the A box (32 rows each, multicast to all four)
 //   mode 3  cluster 2: the two CTAs need the same A box and both load all of it (unicast duplicates)
 //   mode 6  cluster 1, two producer lanes (one issues the A boxes, one the B boxes)
+//   mode 7  cluster 1, stages of TWO k-blocks (4 boxes = 64 KB per iteration, 3 stages): per-iteration or per-byte bound?
 //   mode 4  cluster 1: A only (16 KB per k-block)
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -82,6 +83,24 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const int sub = BOX_ROWS / cs;                  // rows of the shared A box this CTA fetches (multicast modes)
     int s = 0;
     uint32_t ph = 0;
+    if (a.mode == 7) {
+      const int NST = STAGES / 2;
+      for (int tile = 0; tile < a.tiles; ++tile) {
+        const int unit = group + tile * ngroups;
+        const int mb = (unit / a.n_blocks) % a.m_blocks, nb = unit % a.n_blocks;
+        const int row_a = mb * BOX_ROWS, row_b = (nb % (a.n_blocks * 2)) * BOX_ROWS;
+        for (int kb = 0; kb < a.kblocks; kb += 2) {
+          if (tile > 0 || kb >= 2 * NST) wait(&empty[s], ph ^ 1, 1);
+          expect_tx(&full[s], 4 * BOX_BYTES);
+          uint8_t* sa = smem + s * 4 * BOX_BYTES;
+          tma_load(sa, &tm_a, &full[s], kb * BOX_COLS, row_a);
+          tma_load(sa + BOX_BYTES, &tm_a, &full[s], (kb + 1) * BOX_COLS, row_a);
+          tma_load(sa + 2 * BOX_BYTES, &tm_b, &full[s], kb * BOX_COLS, row_b);
+          tma_load(sa + 3 * BOX_BYTES, &tm_b, &full[s], (kb + 1) * BOX_COLS, row_b);
+          if (++s == NST) { s = 0; ph ^= 1; }
+        }
+      }
+    } else
     for (int tile = 0; tile < a.tiles; ++tile) {
       const int unit = group + tile * ngroups;                 // like the GEMM: n fastest
       const int mb = (unit / a.n_blocks) % a.m_blocks, nb = unit % a.n_blocks;
@@ -108,9 +127,11 @@ probe_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const long long c0 = clock64();
     uint32_t eaddr[4];
     for (int r = 0; r < cs; ++r) eaddr[r] = 0;
-    for (int j = 0; j < total; ++j) {
-      const int sj = j % STAGES;
-      wait(&full[sj], (j / STAGES) & 1, 2);
+    const int nst = a.mode == 7 ? STAGES / 2 : STAGES;
+    const int iters = a.mode == 7 ? total / 2 : total;
+    for (int j = 0; j < iters; ++j) {
+      const int sj = j % nst;
+      wait(&full[sj], (j / nst) & 1, 2);
       for (int r = 0; r < cs; ++r) arrive_remote(mapa(smem_u32(&empty[sj]), r));
     }
     const long long c1 = clock64();
@@ -157,9 +178,9 @@ int main() {
   const int smem = STAGES * 2 * BOX_BYTES + 1024 + 256;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  const int modes[6][2] = {{0, 1}, {1, 2}, {2, 4}, {3, 2}, {4, 1}, {6, 1}};
+  const int modes[7][2] = {{0, 1}, {1, 2}, {2, 4}, {3, 2}, {4, 1}, {6, 1}, {7, 1}};
   for (int rep = 0; rep < 2; ++rep)
-    for (int mi = 0; mi < 6; ++mi) {
+    for (int mi = 0; mi < 7; ++mi) {
       const int mode = modes[mi][0], cs = modes[mi][1];
       int grid = 148 / cs * cs;
       if (cs == 4) grid = 144;
