@@ -29,6 +29,10 @@ NVCC_FLAGS = [
 ]
 
 
+if os.environ.get("FERVIT_TL_CHUNKS", "0") not in ("", "0"):
+    NVCC_FLAGS.append("-DFERVIT_TL_CHUNKS")   # per-chunk epilogue stamps for tools/gemm_timeline.py (slows every GEMM 2-3 %)
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
         if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):

@@ -97,6 +97,16 @@ struct Cfg {
 // [0] globaltimer ns at kernel start, [1] at end, [2] clock64 at start, [3] at end (CTA 0, debug bit 8)
 __device__ unsigned long long g_clock_probe[4];
 // debug bit 64: clock64 stamps of the phases of two CTAs (row 0: CTA 0, row 1: leader of the last pair); slots in TL_*
+// The per-chunk stamps of the epilogue (TL_CHUNK) are compiled in only with -DFERVIT_TL_CHUNKS (build.py: env
+// FERVIT_TL_CHUNKS=1): twelve extra predicated stamp sites in the fully unrolled chunk loops cost 2-3 % of every GEMM
+// (instruction-cache pressure in the epilogue; in-graph qkv 18.0 -> 18.4 us, fc1 dgrad 23.4 -> 24.2 us).
+#ifdef FERVIT_TL_CHUNKS
+#define FV_TLC_DECL const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4)
+#define FV_TLC(k) do { if (tlc) TL(TL_CHUNK + 6 * j + (k)); } while (0)
+#else
+#define FV_TLC_DECL do { } while (0)
+#define FV_TLC(k) do { } while (0)
+#endif
 constexpr int TL_N = 64;
 __device__ unsigned long long g_timeline[2][TL_N];
 enum { TL_ENTRY = 0, TL_PROLOGUE = 1, TL_GRIDSYNC = 2, TL_FIRST_FULL = 3, TL_MMA_ISSUED = 4 /* +it, it < 4 */,
@@ -211,8 +221,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           const uint32_t full0 = mapa(smem_u32(&full_bar[stage]), 0);
           tma_load_2d_pair(smem_a + stage * C::A_BYTES, &tm_a, full0, kb * BK, row_a);
           tma_load_2d_pair(smem_b + stage * C::B_BYTES, &tm_b, full0, kb * BK, row_b);
-          if (it == 0 && kb == w.ka) TL(TL_TMA_FIRST);
-          TL(TL_TMA_LAST);
+          if (tl_row >= 0) {   // off the hot path: one predictable branch per k-block
+            if (it == 0 && kb == w.ka) TL(TL_TMA_FIRST);
+            TL(TL_TMA_LAST);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -233,7 +245,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int kb = w.ka; kb < ((p.debug & 3) == 3 ? w.ka : w.ke); ++kb) {
           mbar_wait_parked(&full_bar[stage], phase, 3);
           tc_fence_after();
-          if (it == 0 && kb == w.ka) TL(TL_FIRST_FULL);
+          if (tl_row >= 0 && it == 0 && kb == w.ka) TL(TL_FIRST_FULL);
           if (p.debug & 2) {
             mbar_arrive(&empty_bar[stage]);
             mbar_arrive_cluster(mapa(smem_u32(&empty_bar[stage]), 1));
@@ -403,11 +415,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
         for (int j = 0; j < nch; ++j, ++g) {
           const uint32_t b = g % XB, yb = g & 1;
           const int col = col0 + j * CW;
-          const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4);
+          FV_TLC_DECL;
           if (res) mbar_wait(&my_ld[b], (g / XB) & 1, 5);
-          if (tlc) TL(TL_CHUNK + 6 * j + 0);
+          FV_TLC(0);
           tmem_ld_wait();
-          if (tlc) TL(TL_CHUNK + 6 * j + 1);
+          FV_TLC(1);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -454,10 +466,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               v[i] = drop_keep(dseed, p.drop.site, base + i, p.drop.threshold) ? v[i] * p.drop.scale : 0.0f;
           }
           // the bf16 tile [yb] was last the source of chunk g-2's stores (and, without a residual, the fp32 tile too)
-          if (tlc) TL(TL_CHUNK + 6 * j + 2);
+          FV_TLC(2);
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
-          if (tlc) TL(TL_CHUNK + 6 * j + 3);
+          FV_TLC(3);
           uint8_t* xrow = Xs + b * XT + r * 128;
           if (res) {
 #pragma unroll
@@ -491,7 +503,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (tlc) TL(TL_CHUNK + 6 * j + 4);
+          FV_TLC(4);
           if (lane == 0) {
             if (p.has_out) tma_store_2d(&tm_y, Ys + yb * YT, col, row0);
             if (p.has_f32) tma_store_2d(&tm_x, Xs + b * XT, col, row0);
@@ -501,7 +513,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               issue_load(g + XB, col + (int)XB * CW);
             }
           }
-          if (tlc) TL(TL_CHUNK + 6 * j + 5);
+          FV_TLC(5);
         }
         if (p.lnp_part && row0 + r < p.M) {
           // this warp covered one 128-column part of its rows: {sum, sum of squares} of (v - mref), written once
@@ -566,11 +578,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
               }
             }
           }
-          const bool tlc = (it == 0 && ew == 0 && lane == 0 && j < 4);
+          FV_TLC_DECL;
           if (C::BWD_ACT) mbar_wait(&my_ld[b], (g >> 1) & 1, 5);
-          if (tlc) TL(TL_CHUNK + 6 * j + 0);
+          FV_TLC(0);
           tmem_ld_wait();
-          if (tlc) TL(TL_CHUNK + 6 * j + 1);
+          FV_TLC(1);
           if (j == nch - 1) {
             // last read of this accumulator buffer: hand it back to the MMA issuer before doing the math
             tc_fence_before();
@@ -654,10 +666,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           // the single-buffered output tiles were the source of the previous chunk's stores, issued a whole chunk
           // of TMEM loads and math ago
-          if (tlc) TL(TL_CHUNK + 6 * j + 2);
+          FV_TLC(2);
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          if (tlc) TL(TL_CHUNK + 6 * j + 3);
+          FV_TLC(3);
           if (C::FWD_ACT) {
             uint8_t* zrow = Zs + r * 128;
             if (p.has_z && p.pre_is_deriv) {
@@ -717,14 +729,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           }
           fence_proxy_async_smem();
           __syncwarp();
-          if (tlc) TL(TL_CHUNK + 6 * j + 4);
+          FV_TLC(4);
           if (lane == 0) {
             if (p.has_out) tma_store_2d(&tm_y, Ys, col, row0);
             if (C::FWD_ACT && p.has_z) tma_store_2d(&tm_z, Zs, col, row0);
             tma_store_commit();
             if (C::BWD_ACT && j + 2 < nch) issue_aux(g + 2, col + 2 * CW);  // tile [b] was consumed above
           }
-          if (tlc) TL(TL_CHUNK + 6 * j + 5);
+          FV_TLC(5);
         }
       }
       if (lane == 0 && it < 4) {

@@ -4,6 +4,8 @@
 
 For each batch-256 shape of the ViT-B block the kernel stamps clock64 at its phase boundaries in two CTAs (CTA 0 and
 the leader of the last pair); the table below is in microseconds from kernel entry (SM clock from %globaltimer).
+The per-chunk epilogue stamps ("item 0 chunk j: ...") need a library built with FERVIT_TL_CHUNKS=1
+(`FERVIT_TL_CHUNKS=1 python -m fer_vit_b200.build --force`): they cost 2-3 % of every GEMM and are compiled out by default.
 Results of the GEMM are unaffected by the stamps; timings are of one warm launch with operands resident in L2, the
 situation inside the train step.
 """
