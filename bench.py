@@ -206,7 +206,7 @@ def main():
                                                                 "the GPU (N = 1 only)")
     ap.add_argument("--no-config5", action="store_true", help="skip the global-batch-4096 leg (hybrid only)")
     ap.add_argument("--no-dp-check", action="store_true")
-    ap.add_argument("--buckets", type=int, default=3)
+    ap.add_argument("--buckets", type=int, default=2)
     ap.add_argument("--profile-only", action="store_true", help="run warm-up + the timed steps and exit (for ncu)")
     ap.add_argument("--torch-optim", action="store_true", help="torch.optim.AdamW(fused=True) instead of FusedAdamW")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying "

@@ -88,12 +88,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     want = "\n".join(objs)
     have = open(stamp).read() if os.path.exists(stamp) else ""
     if jobs or force or want != have or not os.path.exists(LIB):
-        cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+        tmp = LIB + ".tmp"   # link beside the target, then rename: a reader never sees a half-written library
+        cmd = [_nvcc(), "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
                "-cudart", "static", "-Xcompiler", "-fPIC"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.replace(tmp, LIB)
         with open(stamp, "w") as fh:
             fh.write(want)
         # stale objects of older source revisions

@@ -32,6 +32,8 @@
 #include "tc_ptx.cuh"
 #include "gemm_tc2_sched.cuh"
 #include <stdlib.h>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 namespace fervit {
@@ -797,8 +799,38 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D tensor map over a row-major [outer, inner] matrix (leading dimension ld elements) of bf16 (esize 2) or fp32
 // (esize 4); out-of-range elements read as zero and are not written.
+// Encoded descriptors are cached by their defining tuple: the plan re-launches the same ~100 GEMM shapes on the same
+// buffers every step (the caching allocator hands the workspace back at the same address), and six
+// cuTensorMapEncodeTiled calls per launch were ~0.6 ms of host time per host-launched step (a graph replay never pays
+// them). Bounded; guarded for the autograd thread.
+namespace {
+struct TmapKey {
+  const void* ptr; uint64_t inner, outer, ld; uint32_t bi, bo; int esize, sw;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && bi == o.bi && bo == o.bo &&
+           esize == o.esize && sw == o.sw;
+  }
+};
+struct TmapHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= (k.inner * 0xD1B54A32D192ED03ull) ^ (k.outer << 17) ^ (k.ld << 29) ^ ((uint64_t)k.bi << 41) ^
+         ((uint64_t)k.bo << 49) ^ ((uint64_t)k.esize << 57) ^ ((uint64_t)k.sw << 7);
+    return (size_t)(h ^ (h >> 31));
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapHash> g_tmap_cache;
+}  // namespace
+
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, uint64_t outer, uint64_t ld,
                  uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  const TmapKey key{ptr, inner, outer, ld, box_inner, box_outer, esize, swizzle_bytes};
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *map = it->second; return 0; }
+  }
   tc2::EncodeTiledFn fn = tc2::encode_fn();
   FV_CHECK(fn != nullptr, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   FV_CHECK((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA operand must be 16-byte aligned");
@@ -816,6 +848,11 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int esize, uint64_t inner, u
                   const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FV_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmap_cache.size() >= 4096) g_tmap_cache.clear();   // a descriptor holds no resource: dropping is free
+    g_tmap_cache.emplace(key, *map);
+  }
   return 0;
 }
 
@@ -1018,8 +1055,6 @@ int gemm_tc2_prof_read(double* us, double* flops, long long* launches, double* p
 // diagnostics (FERVIT_GEMM_DEBUG bit 64): phase stamps of two CTAs of the last CTA-pair GEMM, 2 x 32 values
 int gemm_tc2_timeline(unsigned long long* out, int n) {
   FV_CHECK(n >= 2 * tc2::TL_N, "gemm timeline: need room for %d values", 2 * tc2::TL_N);
-  static bool cleared = false;
-  (void)cleared;
   FV_CUDA(cudaMemcpyFromSymbol(out, tc2::g_timeline, sizeof(unsigned long long) * 2 * tc2::TL_N));
   return 0;
 }

@@ -8,8 +8,11 @@ The native backward writes all gradients of a step into ONE flat fp32 buffer lai
 (head | block 11 ... block 0 | input stage), so a bucket is a contiguous slice. The backward is cut into
 `num_buckets` stage groups; the all-reduce of a finished bucket is launched asynchronously (NCCL's own stream) while
 the next group of blocks is still computing, and the compute stream waits for the buckets only after the last
-group. At this payload the collective is latency-bound (tens of microseconds); 3 buckets is the default, cut so
-that only the input stage's 1.6 MB is exposed after the backward pass (`GradBucketer.stage_groups`).
+group. At this payload the collective is latency-bound (tens of microseconds); the cuts are made from the end so
+that only the input stage's 1.6 MB is exposed after the backward pass (`GradBucketer.stage_groups`). Measured at 8
+GPUs (profiles/r02_buckets_8gpu.jsonl): 1 / 2 / 3 / 4 buckets = 3.443 / 3.434 / 3.460 / 3.499 ms per step at 256 samples
+per GPU — every extra collective costs more (its launch latency and the SMs NCCL takes from the backward GEMMs) than
+its overlap returns, so 2 is the default; models whose whole parameter set trains (77 MB of gradients) may want more.
 """
 from __future__ import annotations
 
@@ -22,7 +25,7 @@ import torch.distributed as dist
 class GradBucketer:
     """Overlapped, bucketed gradient averaging for runtime.PlanRunner.backward()."""
 
-    def __init__(self, process_group: Optional[dist.ProcessGroup] = None, num_buckets: int = 3):
+    def __init__(self, process_group: Optional[dist.ProcessGroup] = None, num_buckets: int = 2):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised")
         self.group = process_group
@@ -75,7 +78,7 @@ def sync_parameters(model: torch.nn.Module, src: int = 0, process_group=None) ->
             dist.broadcast(t, src=src, group=process_group)
 
 
-def enable_data_parallel(model, process_group=None, num_buckets: int = 3, broadcast: bool = True) -> GradBucketer:
+def enable_data_parallel(model, process_group=None, num_buckets: int = 2, broadcast: bool = True) -> GradBucketer:
     """Attach overlapped gradient averaging to a fer_vit_b200 model (any NativeModule)."""
     if broadcast:
         sync_parameters(model, 0, process_group)
