@@ -385,13 +385,14 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             us, fl, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-            rec = (ctypes.c_double * (6 * cap))()
+            rec = (ctypes.c_double * (8 * cap))()
             L.check(lib.fervit_gemm_prof_read(ctypes.byref(us), ctypes.byref(fl), ctypes.byref(n), rec, cap))
             if i == 0:
                 continue
             tot_us += us.value; tot_fl += fl.value; tot_ms += e0.elapsed_time(e1); nl = n.value
+            last_rec = [tuple(rec[8 * j:8 * j + 8]) for j in range(min(n.value, cap))]
             for j in range(min(n.value, cap)):
-                d, f, M_, N_, K_, kd = rec[6 * j:6 * j + 6]
+                d, f, M_, N_, K_, kd = rec[8 * j:8 * j + 6]
                 key = (int(M_), int(N_), int(K_), int(kd))
                 a = by_shape.setdefault(key, [0.0, 0.0, 0])
                 a[0] += d; a[1] += f; a[2] += 1
@@ -413,6 +414,13 @@ def main():
                                (" + fp32 residual stream" if kd >= 16 else ""), "launches_per_step": c // reps,
                                "avg_us": d / c, "tflops": f / (d * 1e-6) / 1e12,
                                "frac_of_peak": f / (d * 1e-6) / 1e12 / pk["tflops_sustained"]})
+            # fc1 -> fc2 (forward) and fc2-dgrad -> fc1-dgrad (backward) are launched back to back with nothing between
+            # them: the time from the first one's last CTA exit to the second one's first CTA past its grid dependency
+            # is the pure kernel-boundary cost inside the graph (PDL edge)
+            seq = sorted(last_rec, key=lambda r: r[6])
+            gaps = [b[6] - a[7] for a, b in zip(seq, seq[1:])
+                    if int(a[3]) == int(b[4]) and int(a[4]) == int(b[3]) and int(a[3]) > int(a[4])
+                    and int(a[5]) % 16 in (1, 2, 5)]
             roof = {"bound": "tensor", "kernel": "tc2::gemm_tc2_kernel (CTA-pair tcgen05.mma cta_group::2 kind::f16, "
                                                  "TMA-fed, TMEM accumulators, TMA-store epilogue: every forward / dgrad GEMM)",
                     "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
@@ -422,6 +430,10 @@ def main():
                     "avg_launch_us": tot_us / reps / nl, "ms_per_step_in_kernel": tot_us / reps / 1e3,
                     "share_of_step": (tot_us / reps / 1e3) / (tot_ms / reps), "step_ms_of_timed_replays": tot_ms / reps,
                     "by_shape": shapes,
+                    "back_to_back_gap_us": ({"median": statistics.median(gaps), "min": min(gaps), "max": max(gaps),
+                                             "pairs": len(gaps), "what": "last CTA exit of fc1 (fc2-dgrad) -> first CTA of "
+                                             "fc2 (fc1-dgrad) past its grid dependency, same replay: the cost of one "
+                                             "kernel boundary inside the graph"} if gaps else None),
                     "how": "in-kernel %globaltimer stamps (min start after the grid dependency, max exit over the CTAs "
                            "of each launch) collected from " + str(reps) + " replays of the step's CUDA graph captured "
                            "with the timer on; share_of_step = sum of the launch durations / the replay's own duration "

@@ -656,6 +656,7 @@ attn_tc_bwd2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
       }
       const float l0 = Ls[r0], l1 = Ls[r1];
       float dsum[2] = {0.f, 0.f};
+      uint32_t kmask = 0u;   // dropout keep bits of this thread's 16 scores: the counter hash runs once per score
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
@@ -665,7 +666,9 @@ attn_tc_bwd2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
           float dpv = dp[nt][e];
           if (drop.threshold) {
             const uint64_t idx = ((uint64_t)bh * S + row) * S + col;
-            dpv = drop_keep(dseed, drop.site, idx, drop.threshold) ? dpv * drop.scale : 0.f;   // dP = dP~ (.) mask
+            const bool keep = drop_keep(dseed, drop.site, idx, drop.threshold);
+            kmask |= (uint32_t)keep << (nt * 4 + e);
+            dpv = keep ? dpv * drop.scale : 0.f;   // dP = dP~ (.) mask
           }
           dsum[e >> 1] += pr * dpv;                                // D_i = sum_j P_ij dP_ij  (= dO_i . O_i)
           c[nt][e] = pr;
@@ -683,11 +686,7 @@ attn_tc_bwd2_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ dout,
         for (int e = 0; e < 4; ++e) {
           ds[e] = c[nt][e] * (dp[nt][e] - dsum[e >> 1]) * scale;   // dS
           pt[e] = c[nt][e];
-          if (drop.threshold) {
-            const int row = (e >> 1) ? r1 : r0, col = nt * 8 + 2 * q + (e & 1);
-            const uint64_t idx = ((uint64_t)bh * S + row) * S + col;
-            pt[e] = drop_keep(dseed, drop.site, idx, drop.threshold) ? pt[e] * drop.scale : 0.f;   // P~
-          }
+          if (drop.threshold) pt[e] = ((kmask >> (nt * 4 + e)) & 1u) ? pt[e] * drop.scale : 0.f;   // P~
         }
         const int col = nt * 8 + 2 * q;
         if (r0 < S) {

@@ -2,8 +2,8 @@
 // 37 tokens), bf16, head dim 32 / 48 / 64. One CTA per (sample, head): Q, K, V (and dO) of the head are staged ONCE in
 // shared memory with cp.async, each warp owns 16-row tiles, every product is a chain of mma.sync m16n8k16 with
 // ldmatrix(.trans) operands (nothing is stored transposed), softmax runs on the accumulator fragments.
-//   forward : per 16-query tile the WHOLE score row (up to 256 keys = 32 n-tiles) lives in registers: plain softmax,
-//             no online rescaling; O = P V with the accumulator fragments of P as A operands.
+//   forward : per 16-query tile two passes over the keys in blocks of 16 (row maximum, then exp / row sum / O += p V with
+//             the accumulator fragments of p as A operands; O is normalised once at the end): no online rescaling.
 //   backward: phase 1, per 16-query tile, walks the keys in blocks of 16: S, dP -> P~, dS (the row statistics come from
 //             the forward pass' LSE and D = rowsum(dO * O)), dQ += dS K. Phase 2, per 16-key tile, walks the queries
 //             in blocks of 16 and recomputes S^T, dP^T so that dV = P~^T dO and dK = dS^T Q accumulate in the
@@ -20,8 +20,6 @@ namespace attn_long {
 
 using namespace attn_frag;
 
-constexpr int FWD_WARPS = 4;
-constexpr int BWD_WARPS = 8;
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
@@ -39,16 +37,21 @@ __device__ __forceinline__ void stage(bf16* dst, const bf16* __restrict__ src, s
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-// NT = key n-tiles of 8 held in registers (SPAD = 8 * NT keys, a multiple of 16)
-template <int HD, int NT>
-__global__ void __launch_bounds__(FWD_WARPS * 32)
+// One warp per 16-query tile (MAXW = the most warps a CTA may have: ceil(S / 16) when that fits, else the tiles are
+// dealt round-robin). Two passes over the keys in blocks of 16 keep the register footprint small enough for two CTAs
+// per SM: pass 1 only finds the row maximum of the scaled scores, pass 2 recomputes the score block, forms
+// p = exp(s - max), accumulates the row sum and O += p V unnormalised; 1 / sum (and the dropout scale) is applied to
+// the 16 x HD output once. The extra Q K^T pass is cheaper than holding the whole score row (104 fp32 registers at
+// S = 197), which capped the kernel at 8 warps per SM.
+template <int HD, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, MAXW <= 13 ? 2 : 1)
 attn_long_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float* __restrict__ lse, int S, int H,
-                     float scale, Dropout drop) {
+                     int SPAD, float scale, Dropout drop) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD, SPAD = NT * 8;
+  constexpr int KS = HD / 16, ND = HD / 8, LD = Lay<HD>::LD;
   pdl_trigger();
   pdl_grid_sync();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int bh = blockIdx.x;
   const int b = bh / H, h = bh % H;
@@ -58,113 +61,123 @@ attn_long_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, float
   bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
   bf16* Ks = Qs + SPAD * LD;
   bf16* Vs = Ks + SPAD * LD;
-  stage<HD>(Qs, Qg, rs, S, SPAD, threadIdx.x, FWD_WARPS * 32);
-  stage<HD>(Ks, Qg + E, rs, S, SPAD, threadIdx.x, FWD_WARPS * 32);
-  stage<HD>(Vs, Qg + 2 * E, rs, S, SPAD, threadIdx.x, FWD_WARPS * 32);
+  stage<HD>(Qs, Qg, rs, S, SPAD, threadIdx.x, blockDim.x);
+  stage<HD>(Ks, Qg + E, rs, S, SPAD, threadIdx.x, blockDim.x);
+  stage<HD>(Vs, Qg + 2 * E, rs, S, SPAD, threadIdx.x, blockDim.x);
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const uint64_t dseed = drop.threshold ? drop.eff() : 0;
   bf16* Og = out + (size_t)b * S * E + h * HD;
+  const int nblk = (S + 15) >> 4;
 #pragma unroll 1
-  for (int mt = warp; mt * 16 < S; mt += FWD_WARPS) {
-    float c[NT][4];
+  for (int mt = warp; mt < nblk; mt += nwarps) {
+    uint32_t aq[KS][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) c[nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      uint32_t a[4];
-      lda<LD>(a, Qs, mt, ks, lane);
-#pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        if (np * 16 < S) {   // skip all-padding key blocks
-          uint32_t bb[4];
-          ldb<LD>(bb, Ks, np, ks, lane);
-          mma16816(c[2 * np], a, bb[0], bb[1]);
-          mma16816(c[2 * np + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
-    // softmax over keys for rows r0 = mt*16+g (elements 0,1) and r1 = r0+8 (elements 2,3)
+    for (int ks = 0; ks < KS; ++ks) lda<LD>(aq[ks], Qs, mt, ks, lane);
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    // ---- pass 1: row maxima (rows r0: elements 0,1; r1: elements 2,3) ----
     float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll 2
+    for (int kb = 0; kb < nblk; ++kb) {
+      float c[2][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + 2 * q + (e & 1);
-        c[nt][e] = col < S ? c[nt][e] * scale : -INFINITY;
-        mx[e >> 1] = fmaxf(mx[e >> 1], c[nt][e]);
+        for (int e = 0; e < 4; ++e) c[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bk[4];
+        ldb<LD>(bk, Ks, kb, ks, lane);
+        mma16816(c[0], aq[ks], bk[0], bk[1]);
+        mma16816(c[1], aq[ks], bk[2], bk[3]);
       }
-    float sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = kb * 16 + nt * 8 + 2 * q + (e & 1);
+          if (col < S) mx[e >> 1] = fmaxf(mx[e >> 1], c[nt][e] * scale);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        c[nt][e] = __expf(c[nt][e] - mx[e >> 1]);
-        sum[e >> 1] += c[nt][e];
-      }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
-      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-    }
-    const int r0 = mt * 16 + g, r1 = r0 + 8;
-    const float inv[2] = {1.0f / sum[0], 1.0f / sum[1]};
-    if (lse && q == 0) {
-      if (r0 < S) lse[(size_t)bh * S + r0] = mx[0] + __logf(sum[0]);
-      if (r1 < S) lse[(size_t)bh * S + r1] = mx[1] + __logf(sum[1]);
-    }
-    if (drop.threshold) {
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int row = (e >> 1) ? r1 : r0, col = nt * 8 + 2 * q + (e & 1);
-          const uint64_t idx = ((uint64_t)bh * S + row) * S + col;
-          c[nt][e] = drop_keep(dseed, drop.site, idx, drop.threshold) ? c[nt][e] * drop.scale : 0.f;
-        }
-    }
-    // O = P V: the accumulator fragments of P are exactly the A fragments of the next MMA
+    // ---- pass 2: p = exp(s - max), row sums, O += p V ----
+    float sum[2] = {0.f, 0.f};
     float o[ND][4];
 #pragma unroll
     for (int nd = 0; nd < ND; ++nd)
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[nd][e] = 0.f;
+#pragma unroll 1
+    for (int kb = 0; kb < nblk; ++kb) {
+      float c[2][4];
 #pragma unroll
-    for (int kk = 0; kk < NT / 2; ++kk) {
-      if (kk * 16 < S) {
-        uint32_t a[4];
-        a[0] = pack_bf16x2(c[2 * kk][0] * inv[0], c[2 * kk][1] * inv[0]);
-        a[1] = pack_bf16x2(c[2 * kk][2] * inv[1], c[2 * kk][3] * inv[1]);
-        a[2] = pack_bf16x2(c[2 * kk + 1][0] * inv[0], c[2 * kk + 1][1] * inv[0]);
-        a[3] = pack_bf16x2(c[2 * kk + 1][2] * inv[1], c[2 * kk + 1][3] * inv[1]);
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-        for (int np = 0; np < ND / 2; ++np) {
-          uint32_t bb[4];
-          ldbt<LD>(bb, Vs, np, kk, lane);
-          mma16816(o[2 * np], a, bb[0], bb[1]);
-          mma16816(o[2 * np + 1], a, bb[2], bb[3]);
+        for (int e = 0; e < 4; ++e) c[nt][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bk[4];
+        ldb<LD>(bk, Ks, kb, ks, lane);
+        mma16816(c[0], aq[ks], bk[0], bk[1]);
+        mma16816(c[1], aq[ks], bk[2], bk[3]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = kb * 16 + nt * 8 + 2 * q + (e & 1);
+          float p = col < S ? __expf(c[nt][e] * scale - mx[e >> 1]) : 0.f;
+          sum[e >> 1] += p;
+          if (drop.threshold) {
+            const uint64_t idx = ((uint64_t)bh * S + ((e >> 1) ? r1 : r0)) * S + col;
+            if (!drop_keep(dseed, drop.site, idx, drop.threshold)) p = 0.f;
+          }
+          c[nt][e] = p;
         }
+      // the accumulator fragments of P are exactly the A fragments of the next MMA
+      uint32_t a[4];
+      a[0] = pack_bf16x2(c[0][0], c[0][1]);
+      a[1] = pack_bf16x2(c[0][2], c[0][3]);
+      a[2] = pack_bf16x2(c[1][0], c[1][1]);
+      a[3] = pack_bf16x2(c[1][2], c[1][3]);
+#pragma unroll
+      for (int np = 0; np < ND / 2; ++np) {
+        uint32_t bb[4];
+        ldbt<LD>(bb, Vs, np, kb, lane);
+        mma16816(o[2 * np], a, bb[0], bb[1]);
+        mma16816(o[2 * np + 1], a, bb[2], bb[3]);
       }
     }
 #pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    }
+    if (lse && q == 0) {
+      if (r0 < S) lse[(size_t)bh * S + r0] = mx[0] + __logf(sum[0]);
+      if (r1 < S) lse[(size_t)bh * S + r1] = mx[1] + __logf(sum[1]);
+    }
+    const float ds = drop.threshold ? drop.scale : 1.0f;
+    const float inv[2] = {ds / sum[0], ds / sum[1]};
+#pragma unroll
     for (int nd = 0; nd < ND; ++nd) {
       const int col = nd * 8 + 2 * q;
-      if (r0 < S) *reinterpret_cast<uint32_t*>(Og + (size_t)r0 * E + col) = pack_bf16x2(o[nd][0], o[nd][1]);
-      if (r1 < S) *reinterpret_cast<uint32_t*>(Og + (size_t)r1 * E + col) = pack_bf16x2(o[nd][2], o[nd][3]);
+      if (r0 < S) *reinterpret_cast<uint32_t*>(Og + (size_t)r0 * E + col) = pack_bf16x2(o[nd][0] * inv[0], o[nd][1] * inv[0]);
+      if (r1 < S) *reinterpret_cast<uint32_t*>(Og + (size_t)r1 * E + col) = pack_bf16x2(o[nd][2] * inv[1], o[nd][3] * inv[1]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-template <int HD>
-__global__ void __launch_bounds__(BWD_WARPS * 32)
+// MAXW = most warps of a CTA: one warp per 16-row tile when ceil(S / 16) <= 13 (both phases in ONE round instead of two
+// uneven ones with 8 warps), else 8 warps taking the tiles round-robin
+// (13 warps put 4 on one SM sub-partition: 16384 / 4 / 32 = 128 registers per thread, a few spilled words at HD = 64)
+template <int HD, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32)
 attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
                      const float* __restrict__ lse, bf16* __restrict__ dqkv, int S, int H, int SPAD, float scale,
                      Dropout drop) {
@@ -188,7 +201,10 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
   bf16* dOs = Vs + MAT;
   float* Ls = reinterpret_cast<float*>(dOs + MAT);
   float* Ds = Ls + SPAD;
-  constexpr int NTH = BWD_WARPS * 32;
+  // dropout keep bits of the head, written by phase 1 and read (transposed) by phase 2 so that the counter hash runs
+  // once per score: byte [(query * nblk + key block) * 4 + q] holds the 4 keys lane q of a quad owns in that block
+  uint8_t* keepb = reinterpret_cast<uint8_t*>(Ds + SPAD);
+  const int NTH = blockDim.x, nwarps = blockDim.x >> 5;
   stage<HD>(Qs, Qg, rs, S, SPAD, threadIdx.x, NTH);
   stage<HD>(Ks, Qg + E, rs, S, SPAD, threadIdx.x, NTH);
   stage<HD>(Vs, Qg + 2 * E, rs, S, SPAD, threadIdx.x, NTH);
@@ -223,7 +239,7 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
 
   // ---------------- phase 1: dQ (rows are queries; the keys are walked in blocks of 16) ----------------
 #pragma unroll 1
-  for (int mt = warp; mt * 16 < S; mt += BWD_WARPS) {
+  for (int mt = warp; mt * 16 < S; mt += nwarps) {
     uint32_t aq[KS][4], ad[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -241,6 +257,7 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
     for (int kb = 0; kb < nblk; ++kb) {
       if (kb * 16 >= S) break;
       float c[2][4], dp[2][4];
+      uint32_t nib[2] = {0u, 0u};
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -264,10 +281,16 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
           float dpv = dp[nt][e];
           if (drop.threshold) {
             const uint64_t idx = ((uint64_t)bh * S + row) * S + col;
-            dpv = drop_keep(dseed, drop.site, idx, drop.threshold) ? dpv * drop.scale : 0.f;
+            const bool keep = drop_keep(dseed, drop.site, idx, drop.threshold);
+            nib[e >> 1] |= (uint32_t)keep << (nt * 2 + (e & 1));
+            dpv = keep ? dpv * drop.scale : 0.f;
           }
           c[nt][e] = p * (dpv - ((e >> 1) ? d1v : d0v)) * scale;   // dS
         }
+      if (drop.threshold) {
+        keepb[(r0 * nblk + kb) * 4 + q] = (uint8_t)nib[0];
+        keepb[(r1 * nblk + kb) * 4 + q] = (uint8_t)nib[1];
+      }
       uint32_t a[4];
       a[0] = pack_bf16x2(c[0][0], c[0][1]);
       a[1] = pack_bf16x2(c[0][2], c[0][3]);
@@ -289,9 +312,11 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
     }
   }
 
+  if (drop.threshold) __syncthreads();   // phase 2 reads the keep bits every warp wrote in phase 1
+
   // ---------------- phase 2: dK, dV (rows are keys j; the queries i are walked in blocks of 16) ----------------
 #pragma unroll 1
-  for (int mt = warp; mt * 16 < S; mt += BWD_WARPS) {
+  for (int mt = warp; mt * 16 < S; mt += nwarps) {
     uint32_t ak[KS][4], av[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
@@ -331,8 +356,9 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
           const float p = (j < S) ? __expf(c[nt][e] * scale - Ls[i]) : 0.f;   // Ls[i >= S] = +inf -> 0
           float ptv = p, dpv = dp[nt][e];
           if (drop.threshold) {
-            const uint64_t idx = ((uint64_t)bh * S + i) * S + j;
-            const bool keep = drop_keep(dseed, drop.site, idx, drop.threshold);
+            // key j sits in block mt at column g (+8): lane g/2 of the quad, bit (g & 1) (+2) of its byte
+            const uint32_t byte = keepb[(i * nblk + mt) * 4 + (g >> 1)];
+            const bool keep = (byte >> ((g & 1) + ((e >> 1) << 1))) & 1u;
             ptv = keep ? p * drop.scale : 0.f;
             dpv = keep ? dpv * drop.scale : 0.f;
           }
@@ -375,46 +401,55 @@ attn_long_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int HD, int NT>
+template <int HD, int MAXW>
 int launch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, Dropout drop, cudaStream_t stream) {
-  constexpr int smem = 3 * NT * 8 * Lay<HD>::LD * 2;
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
-    FV_CUDA(cudaFuncSetAttribute(attn_long_fwd_kernel<HD, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
+  const int SPAD = (S + 15) / 16 * 16;
+  const int smem = 3 * SPAD * Lay<HD>::LD * 2;
+  static int smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    FV_CUDA(cudaFuncSetAttribute(attn_long_fwd_kernel<HD, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
   }
+  const int tiles = SPAD / 16;
+  const int warps = tiles < MAXW ? tiles : MAXW;
   const float scale = 1.0f / sqrtf((float)HD);
   ProfScope prof(1, (double)B * S * H * HD * 4.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  FV_CUDA(launch_pdl(attn_long_fwd_kernel<HD, NT>, dim3(B * H), dim3(FWD_WARPS * 32), (size_t)smem, stream, qkv, out, lse,
-                     S, H, scale, drop));
+  FV_CUDA(launch_pdl(attn_long_fwd_kernel<HD, MAXW>, dim3(B * H), dim3(warps * 32), (size_t)smem, stream, qkv, out, lse,
+                     S, H, SPAD, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
 }
 template <int HD>
 int dispatch_fwd(const bf16* qkv, bf16* out, float* lse, int B, int S, int H, Dropout drop, cudaStream_t stream) {
-  if (S <= 64) return launch_fwd<HD, 8>(qkv, out, lse, B, S, H, drop, stream);
-  if (S <= 128) return launch_fwd<HD, 16>(qkv, out, lse, B, S, H, drop, stream);
-  if (S <= 208) return launch_fwd<HD, 26>(qkv, out, lse, B, S, H, drop, stream);
-  return launch_fwd<HD, 32>(qkv, out, lse, B, S, H, drop, stream);
+  if (S <= 208) return launch_fwd<HD, 13>(qkv, out, lse, B, S, H, drop, stream);
+  return launch_fwd<HD, 16>(qkv, out, lse, B, S, H, drop, stream);
 }
-template <int HD>
-int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
-               Dropout drop, cudaStream_t stream) {
+template <int HD, int MAXW>
+int launch_bwd_w(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
+                 Dropout drop, cudaStream_t stream) {
   const int SPAD = (S + 15) / 16 * 16;
-  const int smem = 4 * SPAD * Lay<HD>::LD * 2 + 2 * SPAD * 4;
+  const int smem = 4 * SPAD * Lay<HD>::LD * 2 + 2 * SPAD * 4 + (drop.threshold ? SPAD * (SPAD / 16) * 4 : 0);
   static int smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    FV_CUDA(cudaFuncSetAttribute(attn_long_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FV_CUDA(cudaFuncSetAttribute(attn_long_bwd_kernel<HD, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
+  const int tiles = SPAD / 16;
+  const int warps = tiles < MAXW ? tiles : MAXW;
   const float scale = 1.0f / sqrtf((float)HD);
   ProfScope prof(1, (double)B * S * H * HD * 8.0 * sizeof(bf16) + (double)B * H * S * 4.0, stream);
-  FV_CUDA(launch_pdl(attn_long_bwd_kernel<HD>, dim3(B * H), dim3(BWD_WARPS * 32), (size_t)smem, stream, qkv, out, dout,
+  FV_CUDA(launch_pdl(attn_long_bwd_kernel<HD, MAXW>, dim3(B * H), dim3(warps * 32), (size_t)smem, stream, qkv, out, dout,
                      lse, dqkv, S, H, SPAD, scale, drop));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
+}
+template <int HD>
+int launch_bwd(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, int B, int S, int H,
+               Dropout drop, cudaStream_t stream) {
+  if (S <= 208) return launch_bwd_w<HD, 13>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);
+  return launch_bwd_w<HD, 8>(qkv, out, dout, lse, dqkv, B, S, H, drop, stream);
 }
 
 }  // namespace attn_long

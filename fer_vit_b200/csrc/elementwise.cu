@@ -47,34 +47,72 @@ struct WcBatch {
   bf16* dst[WC_BATCH];
   bf16* dst_t[WC_BATCH];
   int R[WC_BATCH], C[WC_BATCH];
-  int tile0[WC_BATCH + 1];  // first 32x32 tile of each matrix in the flat grid
+  int tile0[WC_BATCH + 1];  // first 64x64 tile of each matrix in the flat grid
   int n;
 };
-__global__ void weight_cache_batch_kernel(const __grid_constant__ WcBatch b) {
-  __shared__ float tile[32][33];
+// 64 x 64 tiles, 256 threads: float4 loads, 8-byte row-major stores, and the transposed copy written as bf16 pairs
+// along r (one warp = 128 contiguous bytes of one transposed row). Matrices whose shape or alignment does not allow the
+// vector forms take the element-wise path of the same tile.
+__global__ void __launch_bounds__(256) weight_cache_batch_kernel(const __grid_constant__ WcBatch b) {
+  __shared__ float tile[64][65];
   int m = 0;
   while (m + 1 < b.n && (int)blockIdx.x >= b.tile0[m + 1]) ++m;
   const int R = b.R[m], C = b.C[m];
   const int t = blockIdx.x - b.tile0[m];
-  const int tiles_c = (C + 31) / 32;
-  const int c0 = (t % tiles_c) * 32, r0 = (t / tiles_c) * 32;
+  const int tiles_c = (C + 63) / 64;
+  const int c0 = (t % tiles_c) * 64, r0 = (t / tiles_c) * 64;
   const float* __restrict__ src = b.src[m];
   bf16* __restrict__ dst = b.dst[m];
   bf16* __restrict__ dst_t = b.dst_t[m];
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    float v = 0.f;
-    if (r < R && c < C) {
-      v = src[(size_t)r * C + c];
-      if (dst) dst[(size_t)r * C + c] = __float2bfloat16_rn(v);
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                   (dst == nullptr || (reinterpret_cast<uintptr_t>(dst) & 7) == 0);
+  if (vec) {
+    const int cq = (tid & 15) * 4;           // 16 threads cover the 64 columns of a row
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = i * 16 + (tid >> 4);
+      const int r = r0 + rr, c = c0 + cq;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < R && c < C) {
+        v = *reinterpret_cast<const float4*>(src + (size_t)r * C + c);
+        if (dst) {
+          uint2 o;
+          o.x = pack_bf16x2(v.x, v.y);
+          o.y = pack_bf16x2(v.z, v.w);
+          *reinterpret_cast<uint2*>(dst + (size_t)r * C + c) = o;
+        }
+      }
+      tile[rr][cq] = v.x; tile[rr][cq + 1] = v.y; tile[rr][cq + 2] = v.z; tile[rr][cq + 3] = v.w;
     }
-    tile[i][threadIdx.x] = v;
+  } else {
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int rr = i >> 6, cc = i & 63;
+      const int r = r0 + rr, c = c0 + cc;
+      float v = 0.f;
+      if (r < R && c < C) {
+        v = src[(size_t)r * C + c];
+        if (dst) dst[(size_t)r * C + c] = __float2bfloat16_rn(v);
+      }
+      tile[rr][cc] = v;
+    }
   }
   __syncthreads();
-  if (dst_t) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int c = c0 + i, r = r0 + threadIdx.x;
-      if (r < R && c < C) dst_t[(size_t)c * R + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  if (!dst_t) return;
+  if ((R % 2 == 0) && ((reinterpret_cast<uintptr_t>(dst_t) & 3) == 0)) {
+    const int rr = threadIdx.x * 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int cc = i * 8 + threadIdx.y;
+      const int c = c0 + cc, r = r0 + rr;
+      if (c < C && r < R)   // R even, r even: r + 1 < R
+        *reinterpret_cast<uint32_t*>(dst_t + (size_t)c * R + r) = pack_bf16x2(tile[rr][cc], tile[rr + 1][cc]);
+    }
+  } else {
+    for (int i = tid; i < 64 * 64; i += 256) {
+      const int cc = i >> 6, rr = i & 63;
+      const int c = c0 + cc, r = r0 + rr;
+      if (c < C && r < R) dst_t[(size_t)c * R + r] = __float2bfloat16_rn(tile[rr][cc]);
     }
   }
 }
@@ -225,21 +263,32 @@ colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int 
   const float4 t = colsum_block_reduce(acc, red);
   if (threadIdx.y == 0 && c < C) *reinterpret_cast<float4*>(partial + (size_t)blockIdx.y * C + c) = t;
 }
+// finishing pass, block (8, 32): one CTA per 32 columns (x = group of 4 columns), 32 row lanes walk the partial rows, so
+// even 256 partial rows are 8 independent loads per thread; the row lanes are combined in a fixed order
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const float* alpha_ptr, float alpha,
                     float* __restrict__ out) {
-  __shared__ float4 red[8][32];
-  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  __shared__ float4 red[32][8];
+  pdl_trigger();
+  pdl_grid_sync();
+  const int c = (blockIdx.x * 8 + threadIdx.x) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < C) {
-#pragma unroll 4
-    for (int k = threadIdx.y; k < chunks; k += 8) {
+#pragma unroll 8
+    for (int k = threadIdx.y; k < chunks; k += 32) {
       const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)k * C + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  const float4 t = colsum_block_reduce(acc, red);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
   if (threadIdx.y == 0 && c < C) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int y = 0; y < 32; ++y) {
+      const float4 v = red[y][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
     if (alpha_ptr) alpha *= __ldg(alpha_ptr);
     *reinterpret_cast<float4*>(out + c) = make_float4(t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha);
   }
@@ -248,6 +297,8 @@ colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const 
 // ---- split-K reduction: out[i] = alpha * sum_s partial[s][i] ----
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, size_t n4, const float* alpha_ptr,
                                      float alpha, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_grid_sync();
   if (alpha_ptr) alpha *= __ldg(alpha_ptr);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -400,7 +451,7 @@ int weight_cache_batch(const float* const* src, const int* R, const int* C, bf16
       b.src[i] = src[base + i]; b.dst[i] = dst[base + i]; b.dst_t[i] = dst_t[base + i];
       b.R[i] = R[base + i]; b.C[i] = C[base + i];
       b.tile0[i] = tiles;
-      tiles += ceil_div(R[base + i], 32) * ceil_div(C[base + i], 32);
+      tiles += ceil_div(R[base + i], 64) * ceil_div(C[base + i], 64);
     }
     b.tile0[b.n] = tiles;
     if (tiles == 0) continue;
@@ -484,7 +535,8 @@ int colsum(const T* in, int R, int C, long long ld, float* scratch, const float*
   dim3 grid(ceil_div(C, 128), chunks), block(32, 8);
   FV_CUDA(launch_pdl(ew::colsum_partial_kernel<T>, grid, block, 0, stream, in, R, C, ld, rpc, scratch, drop));
   FV_COUNT_LAUNCH();
-  ew::colsum_final_kernel<<<ceil_div(C, 128), block, 0, stream>>>(scratch, chunks, C, alpha_ptr, alpha, out);
+  FV_CUDA(launch_pdl(ew::colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(8, 32), 0, stream, (const float*)scratch, chunks,
+                     C, alpha_ptr, alpha, out));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -496,7 +548,8 @@ template int colsum<bf16>(const bf16*, int, int, long long, float*, const float*
 
 int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream) {
   FV_CHECK(C % 4 == 0, "colsum_reduce_partials: column count must be a multiple of 4");
-  ew::colsum_final_kernel<<<ceil_div(C, 128), dim3(32, 8), 0, stream>>>(partial, chunks, C, nullptr, 1.0f, out);
+  FV_CUDA(launch_pdl(ew::colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(8, 32), 0, stream, partial, chunks, C,
+                     (const float*)nullptr, 1.0f, out));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -505,7 +558,8 @@ int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, 
 int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
                   cudaStream_t stream) {
   FV_CHECK(n % 4 == 0, "splitk_reduce: element count must be a multiple of 4");
-  ew::splitk_reduce_kernel<<<ew::grid_for(n / 4, 64), 64, 0, stream>>>(partial, splits, n / 4, alpha_ptr, alpha, out);
+  FV_CUDA(launch_pdl(ew::splitk_reduce_kernel, dim3(ew::grid_for(n / 4, 64)), dim3(64), 0, stream, partial, splits,
+                     n / 4, alpha_ptr, alpha, out));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

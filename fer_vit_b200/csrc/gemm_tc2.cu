@@ -1030,21 +1030,26 @@ int gemm_tc2_prof(int op, cudaStream_t stream) {
   return 0;
 }
 // Sum over the slots (blocking copy): device microseconds, FLOPs, launches; optionally one record per launch
-// ({us, flops, M, N, K, kind}, `cap` records of 6 doubles).
+// ({us, flops, M, N, K, kind, start_us, end_us}, `cap` records of 8 doubles; launch order).
 int gemm_tc2_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap) {
   const int n = tc2::g_prof_next;
   std::vector<unsigned long long> h(2 * (size_t)(n > 0 ? n : 1));
   if (n > 0) FV_CUDA(cudaMemcpyFromSymbol(h.data(), tc2::g_prof_ts, sizeof(unsigned long long) * 2 * n));
   double t = 0, f = 0;
   long long cnt = 0;
+  unsigned long long t0 = ~0ull;
+  for (int i = 0; i < n; ++i)
+    if (h[2 * i] != ~0ull && h[2 * i + 1] >= h[2 * i] && h[2 * i] < t0) t0 = h[2 * i];
   for (int i = 0; i < n; ++i) {
     if (h[2 * i] == ~0ull || h[2 * i + 1] < h[2 * i]) continue;   // slot not run since the last reset
     const double d = (double)(h[2 * i + 1] - h[2 * i]) * 1e-3;
     t += d; f += tc2::g_prof_flops[i];
     if (per_launch && cnt < cap) {
-      double* r = per_launch + 6 * cnt;
+      double* r = per_launch + 8 * cnt;
       r[0] = d; r[1] = tc2::g_prof_flops[i];
       for (int k = 0; k < 4; ++k) r[2 + k] = tc2::g_prof_shape[i][k];
+      r[6] = (double)(h[2 * i] - t0) * 1e-3;        // start and end, microseconds after the first launch's start
+      r[7] = (double)(h[2 * i + 1] - t0) * 1e-3;
     }
     ++cnt;
   }

@@ -359,7 +359,8 @@ int fervit_debug_gemm_clock(double* ns, double* cycles);
  * parallel branches intact — host-side events cannot sit there). op 1: on, restart slot numbering; op 2: clear the
  * stamps recorded so far (async on `stream`, enqueue before the replay to be timed); op 0: off.
  * read: sum over the slots stamped since the last clear — device microseconds, FLOPs (2MNK), launches; per_launch
- * (optional, cap records of 6 doubles): {us, flops, M, N, K, epilogue kind + 16 * fp32 variant}. */
+ * (optional, cap records of 8 doubles, in launch order): {us, flops, M, N, K, epilogue kind + 16 * fp32 variant, start, end
+ * in microseconds after the first launch's start}. */
 int fervit_gemm_prof(int op, void* stream);
 int fervit_gemm_prof_read(double* us, double* flops, long long* launches, double* per_launch, int cap);
 

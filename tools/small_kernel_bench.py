@@ -38,6 +38,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=24)
+    ap.add_argument("--seq", type=int, default=19, help="tokens per sample (197 = ImageViT, config 2)")
+    ap.add_argument("--heads", type=int, default=12)
+    ap.add_argument("--drop", type=float, default=0.0, help="dropout on the attention weights")
     a = ap.parse_args()
     peak = 6551.7
     try:
@@ -45,8 +48,8 @@ def main():
     except Exception:
         pass
     lib = L.lib()
-    B, S, H, hd = a.batch, 19, 12, 64
-    E, T = H * hd, a.batch * 19
+    B, S, H, hd = a.batch, a.seq, a.heads, 64
+    E, T = H * hd, a.batch * a.seq
     n = 8                                                   # buffer sets in rotation: 8 x ~60 MB > L2
     st = lambda: torch.cuda.current_stream().cuda_stream
     bf = torch.bfloat16
@@ -65,13 +68,13 @@ def main():
 
     def attn_fwd(i):
         k = i % n
-        L.check(lib.fervit_attention_forward(L.BF16, qkv[k].data_ptr(), B, S, H, hd, 0.0, 0, 0, out[k].data_ptr(),
+        L.check(lib.fervit_attention_forward(L.BF16, qkv[k].data_ptr(), B, S, H, hd, a.drop, 1234, 7, out[k].data_ptr(),
                                              lse[k].data_ptr(), st()))
 
     def attn_bwd(i):
         k = i % n
         L.check(lib.fervit_attention_backward(L.BF16, qkv[k].data_ptr(), out[k].data_ptr(), dout[k].data_ptr(),
-                                              lse[k].data_ptr(), B, S, H, hd, 0.0, 0, 0, dqkv[k].data_ptr(), st()))
+                                              lse[k].data_ptr(), B, S, H, hd, a.drop, 1234, 7, dqkv[k].data_ptr(), st()))
 
     def ln_fwd(i):
         k = i % n
@@ -94,7 +97,7 @@ def main():
     for name, fn, nbytes in cases:
         us = replay_us(fn, a.iters)
         gbs = nbytes / us / 1e3
-        print(json.dumps({"kernel": name, "batch": B, "us": round(us, 2), "algorithmic_mb": round(nbytes / 1e6, 1),
+        print(json.dumps({"kernel": name, "batch": B, "seq": S, "heads": H, "attn_dropout": a.drop, "us": round(us, 2), "algorithmic_mb": round(nbytes / 1e6, 1),
                           "achieved_gbs": round(gbs, 1), "peak_gbs": peak, "frac": round(gbs / peak, 3)}), flush=True)
 
 
