@@ -578,6 +578,21 @@ int colsum_partial(const T* in, int R, int C, long long ld, float* scratch, cuda
   FV_LAUNCH_CHECK();
   return 0;
 }
+// the same with the chunk height given: scratch [ceil(R / rows_per_chunk)][C] (grouped column sums: R = groups x rows,
+// rows_per_chunk dividing the group height keeps every chunk inside one group)
+template <typename T>
+int colsum_partial_rows(const T* in, int R, int C, long long ld, int rows_per_chunk, float* scratch, cudaStream_t stream) {
+  FV_CHECK(C % 4 == 0 && ld % 4 == 0 && rows_per_chunk > 0, "colsum_partial_rows: bad shape");
+  dim3 grid(ceil_div(C, 128), ceil_div(R, rows_per_chunk)), block(32, 8);
+  FV_CHECK(grid.y <= 65535, "colsum_partial_rows: too many chunks");
+  FV_CUDA(launch_pdl(ew::colsum_partial_kernel<T>, grid, block, 0, stream, in, R, C, ld, rows_per_chunk, scratch,
+                     make_dropout(0.f, 0, 0)));
+  FV_COUNT_LAUNCH();
+  FV_LAUNCH_CHECK();
+  return 0;
+}
+template int colsum_partial_rows<float>(const float*, int, int, long long, int, float*, cudaStream_t);
+template int colsum_partial_rows<bf16>(const bf16*, int, int, long long, int, float*, cudaStream_t);
 template int colsum_partial<float>(const float*, int, int, long long, float*, cudaStream_t);
 template int colsum_partial<bf16>(const bf16*, int, int, long long, float*, cudaStream_t);
 

@@ -68,6 +68,8 @@ int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha
                   cudaStream_t stream);
 template <typename T>
 int colsum_partial(const T* in, int R, int C, long long ld, float* scratch, cudaStream_t stream);
+template <typename T>
+int colsum_partial_rows(const T* in, int R, int C, long long ld, int rows_per_chunk, float* scratch, cudaStream_t stream);
 // deferred AdapterModule gradient finalisation (see elementwise.cu)
 constexpr int AD_FIN_MAX = 16;
 struct AdapterGradJob {

@@ -67,6 +67,13 @@ struct Bufs {
   // per-block partial sums of the AdapterModule gradients, finished once per backward stage group
   struct AdParts { float *w2_part, *w1_part, *cs_dy, *cs_du; int s2, s1, chunks; };
   std::vector<AdParts> ad;
+  // deferred form (ad_deferred()): the adapters' dy / du / g / x of ALL blocks sit in contiguous pools [depth][T][.], so
+  // that one split-K launch per weight and one column-sum launch per bias serve every block of a backward call
+  bool ad_defer = false;
+  void *ad_dy_pool = nullptr, *ad_du_pool = nullptr;     // [depth][T][E], [depth][T][A] act
+  float *ad_w2_pool = nullptr, *ad_w1_pool = nullptr;    // [ad_slabs][E*A] split-K slabs
+  float *ad_csdy_pool = nullptr, *ad_csdu_pool = nullptr;  // [depth][AD_CPB][E], [depth][AD_CPB][A]
+  int ad_slabs = 0;
   float* ad_fin;               // scratch of adapter_grad_finalize
   float* head_scratch;         // partial sums of the head's parameter gradients (own buffer: may run on the side stream)
   float* scratch;
@@ -194,6 +201,38 @@ int wgrad_splits(bool bf16_mode, int Nout, int Kin, int T) {
   return gemm_f32_simt_effective_splits(T, s);
 }
 
+// Deferred AdapterModule gradients (bf16, pre-norm, fused adapter kernel, T a multiple of the GEMM's k-block): instead
+// of four small launches per block beside the main chain, every block's dy and du are kept and ONE split-K GEMM per
+// weight (K = blocks x T, each split inside one block) plus ONE column-sum launch per bias finish all blocks of the
+// backward call. FERVIT_ADAPTER_DEFER=0 restores the per-block form.
+constexpr int AD_CPB = 16;   // column-sum chunks per block
+bool ad_deferred(const fervit_plan* p, int B, bool save) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("FERVIT_ADAPTER_DEFER"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  const fervit_config& c = p->cfg;
+  const long long T = (long long)B * p->S;
+  return on == 1 && save && c.mode == FERVIT_BF16 && c.norm_first && c.adapter_dim > 0 && T % 64 == 0 &&
+         T % AD_CPB == 0 && adapter_fused_supported((int)T, c.E, c.adapter_dim);
+}
+// split-K slabs per block for n blocks: the divisor d of T / 64 (at least 4 k-blocks per split) that minimises
+// waves x (k-blocks per split + ~8 k-blocks' worth of ramp and epilogue) for tiles x n x d work units
+int ad_defer_spb(int n, int T, int tiles) {
+  const int kb = T / 64, sms = num_sms();
+  int best = 1;
+  long long best_cost = -1;
+  for (int d = 1; d <= kb; ++d) {
+    if (kb % d || (kb / d < 4 && d > 1)) continue;
+    const long long units = (long long)tiles * n * d;
+    const long long cost = ((units + sms - 1) / sms) * (kb / d + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = d; }
+  }
+  return best;
+}
+int ad_defer_slabs(const fervit_plan* p) {
+  const int a = 4 * num_sms() / 6 + 1;   // more than ad_defer_spb() ever picks for 6 tiles; the caller clamps anyway
+  return a > p->cfg.depth ? a : p->cfg.depth;
+}
+
 size_t scratch_floats_for(const fervit_plan* p, int B) {
   const fervit_config& c = p->cfg;
   const bool bf = c.mode == FERVIT_BF16;
@@ -236,6 +275,12 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
     b.x_at[i] = (post && bf) ? xas[i % nx] : (void*)b.x[i];
   }
   b.blk.resize(c.depth);
+  b.ad_defer = ad_deferred(p, B, save);
+  AT *x2_pool = nullptr, *ga_pool = nullptr;
+  if (b.ad_defer) {
+    x2_pool = ar.take<AT>((size_t)c.depth * T * E);
+    ga_pool = ar.take<AT>((size_t)c.depth * T * A);
+  }
   BlockBufs shared{};
   for (int i = 0; i < c.depth; ++i) {
     BlockBufs k{};
@@ -251,9 +296,9 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
       k.g1 = ar.take<AT>(T * F);
       k.rr2 = post ? ar.take<float>(T * E) : nullptr;
       if (A) {
-        k.x2_at = ar.take<AT>(T * E);
+        k.x2_at = b.ad_defer ? (void*)(x2_pool + (size_t)i * T * E) : (void*)ar.take<AT>(T * E);
         k.ua = ar.take<AT>(T * A);
-        k.ga = ar.take<AT>(T * A);
+        k.ga = b.ad_defer ? (void*)(ga_pool + (size_t)i * T * A) : (void*)ar.take<AT>(T * A);
       }
       shared = k;
     } else {
@@ -277,7 +322,17 @@ void carve(const fervit_plan* p, int B, bool save, Arena& ar, Bufs& b) {
     b.d_big = ar.take<AT>(T * (3 * E > F ? 3 * E : F));
     b.d_e1 = ar.take<AT>(T * E);
     b.d_e2 = ar.take<AT>(T * E);
-    if (A) {
+    if (A && b.ad_defer) {
+      b.du_ad = nullptr;
+      b.ad_dy_pool = ar.take<AT>((size_t)c.depth * T * E);
+      b.ad_du_pool = ar.take<AT>((size_t)c.depth * T * A);
+      b.ad_slabs = ad_defer_slabs(p);
+      b.ad_w2_pool = ar.take<float>((size_t)b.ad_slabs * E * A);
+      b.ad_w1_pool = ar.take<float>((size_t)b.ad_slabs * E * A);
+      b.ad_csdy_pool = ar.take<float>((size_t)c.depth * AD_CPB * E);
+      b.ad_csdu_pool = ar.take<float>((size_t)c.depth * AD_CPB * A);
+      b.ad_fin = ar.take<float>((size_t)adapter_grad_finalize_scratch_floats());
+    } else if (A) {
       b.du_ad = ar.take<AT>(T * A);
       b.ad.resize(c.depth);
       for (int i = 0; i < c.depth; ++i) {
@@ -563,6 +618,11 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   auto GB = [&](int blk, int s) -> float* { return G[p->bslot(blk, s)]; };
   const Dropout nodrop = cx.none();
   std::vector<AdapterGradJob> ad_jobs;  // adapters whose partial gradients were produced in this call
+  // deferred form: the bf16 gradient ENTERING block i's stage (written by the head or by block i+1's norm1 backward) and
+  // the adapter's du live in per-block pool slots; ad_lo..ad_hi = blocks of this call whose adapter gradients are due
+  auto AD_DY = [&](int blk) { return (AT*)b.ad_dy_pool + (size_t)blk * T * E; };
+  auto AD_DU = [&](int blk) { return (AT*)b.ad_du_pool + (size_t)blk * T * A; };
+  int ad_lo = c.depth, ad_hi = -1;
   bool side_pending = false;            // side-stream work of the current block not yet joined
   bool side_used = false;               // anything at all went to the side stream in this call
 
@@ -585,7 +645,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       }
       FV_TRY(head_bwd<AT>(b.x[c.depth], dlogits, B, S, E, p->P(FERVIT_G_HEAD_LN_W), p->P(FERVIT_G_HEAD_LN_B),
                           p->P(FERVIT_G_HEAD_W), c.C, b.head_mean, b.head_rstd, dh, b.dx[0],
-                          F32 ? nullptr : (AT*)b.dx_at[0], wg, b.head_scratch, G[FERVIT_G_HEAD_W],
+                          F32 ? nullptr : (b.ad_defer ? AD_DY(c.depth - 1) : (AT*)b.dx_at[0]), wg, b.head_scratch,
+                          G[FERVIT_G_HEAD_W],
                           G[FERVIT_G_HEAD_LN_W], G[FERVIT_G_HEAD_LN_B], G[FERVIT_G_HEAD_B], st, hs));
     } else if (stage <= c.depth) {
       const int i = c.depth - stage;
@@ -603,9 +664,10 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           if (fused) {
             // du = alpha * (dy W2) * gelu'(u) and dx = dy + du W1 in one tensor-core kernel (adapter_tc.cu)
             if constexpr (!F32)
-              FV_TRY(adapter_fused(1, (const bf16*)DXA(cur), p->WBT(p->bslot(i, FERVIT_B_AD2_W)),
-                                   p->WBT(p->bslot(i, FERVIT_B_AD1_W)), DX(cur), nullptr, nullptr,
-                                   p->PB(i, FERVIT_B_ALPHA), (const bf16*)k.ua, (bf16*)b.du_ad, nullptr, DX(cur ^ 1),
+              FV_TRY(adapter_fused(1, (const bf16*)(b.ad_defer ? AD_DY(i) : DXA(cur)),
+                                   p->WBT(p->bslot(i, FERVIT_B_AD2_W)), p->WBT(p->bslot(i, FERVIT_B_AD1_W)), DX(cur),
+                                   nullptr, nullptr, p->PB(i, FERVIT_B_ALPHA), (const bf16*)k.ua,
+                                   (bf16*)(b.ad_defer ? AD_DU(i) : (AT*)b.du_ad), nullptr, DX(cur ^ 1),
                                    (bf16*)ATOUT(cur ^ 1), T, E, st));
           } else {
             // du = alpha * (dy W2) * gelu'(u): one GEMM, derivative and alpha in its epilogue
@@ -615,6 +677,11 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           if (GB(i, FERVIT_B_AD2_W)) {
             FV_CHECK(GB(i, FERVIT_B_AD2_B) && GB(i, FERVIT_B_AD1_W) && GB(i, FERVIT_B_AD1_B) && GB(i, FERVIT_B_ALPHA),
                      "backward: adapter gradients must be requested together");
+            if (b.ad_defer) {   // nothing now: one grouped launch per weight / bias at the end of this call
+              FV_CHECK(fused, "backward: deferred adapter gradients need the fused adapter kernel");
+              if (i < ad_lo) ad_lo = i;
+              if (i > ad_hi) ad_hi = i;
+            } else {
             // partial sums only; adapter_grad_finalize() below finishes all blocks of this stage group at once.
             // They read dy (DX/DXA(cur)) and du, which the main chain overwrites only at norm2's backward: fork
             // here, join there.
@@ -643,6 +710,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
             job.db1 = GB(i, FERVIT_B_AD1_B); job.dalpha = GB(i, FERVIT_B_ALPHA);
             job.s2 = q.s2; job.s1 = q.s1; job.chunks = q.chunks; job.E = E; job.A = A;
             ad_jobs.push_back(job);
+            }
           }
           if (!fused) {
             e = make_epilogue();
@@ -709,8 +777,10 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         {
           float* part = GB(i, FERVIT_B_LN1_W) ? b.scratch : nullptr;
           const float* g1 = (!F32 && p->fold1[i]) ? nullptr : p->PB(i, FERVIT_B_LN1_W);
+          // deferred adapter gradients: the act copy is the dy of block i-1's adapter and goes to that block's slot
+          AT* at_out = (b.ad_defer && i > 0) ? AD_DY(i - 1) : ATOUT(cur ^ 1);
           FV_TRY((layernorm_bwd<AT, AT>((const AT*)b.d_e1, b.x[i], k.m1, k.r1, g1, DX(cur), T, E,
-                                        DX(cur ^ 1), ATOUT(cur ^ 1), part, nodrop, st)));
+                                        DX(cur ^ 1), at_out, part, nodrop, st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
             FV_TRY(colsum_reduce_partials(part, g, 2 * E, b.scratch + (size_t)g * 2 * E, st));
@@ -826,6 +896,34 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
   if (side_used) {  // everything forked in this call is complete before the gradients are finalised / handed out
     FV_CUDA(cudaEventRecord(p->ev_tail, p->side));
     FV_CUDA(cudaStreamWaitEvent(st, p->ev_tail, 0));
+  }
+  if (ad_hi >= ad_lo) {
+    if constexpr (!F32) {
+      // blocks ad_lo..ad_hi are contiguous in the pools: K = n*T rows, every split / chunk inside one block
+      const int n = ad_hi - ad_lo + 1;
+      int spb = ad_defer_spb(n, T, 6);
+      while (n * spb > b.ad_slabs && spb > 1) --spb;
+      while ((T / 64) % spb) --spb;
+      const int rpc = T / AD_CPB;
+      FV_TRY(wgrad_partial<AT>(cx, AD_DY(ad_lo), E, (const AT*)b.blk[ad_lo].ga, A, n * T, n * spb, b.ad_w2_pool));
+      FV_TRY(wgrad_partial<AT>(cx, AD_DU(ad_lo), A, (const AT*)b.blk[ad_lo].x2_at, E, n * T, n * spb, b.ad_w1_pool));
+      FV_TRY(colsum_partial_rows<AT>(AD_DY(ad_lo), n * T, E, E, rpc, b.ad_csdy_pool, st));
+      FV_TRY(colsum_partial_rows<AT>(AD_DU(ad_lo), n * T, A, A, rpc, b.ad_csdu_pool, st));
+      for (int i = ad_lo; i <= ad_hi; ++i) {
+        const int g = i - ad_lo;
+        AdapterGradJob job;
+        job.w2_part = b.ad_w2_pool + (size_t)g * spb * E * A;
+        job.w1_part = b.ad_w1_pool + (size_t)g * spb * E * A;
+        job.cs_dy = b.ad_csdy_pool + (size_t)g * AD_CPB * E;
+        job.cs_du = b.ad_csdu_pool + (size_t)g * AD_CPB * A;
+        job.W2 = p->PB(i, FERVIT_B_AD2_W); job.b2 = p->PB(i, FERVIT_B_AD2_B);
+        job.alpha_ptr = p->PB(i, FERVIT_B_ALPHA);
+        job.dW2 = GB(i, FERVIT_B_AD2_W); job.dW1 = GB(i, FERVIT_B_AD1_W); job.db2 = GB(i, FERVIT_B_AD2_B);
+        job.db1 = GB(i, FERVIT_B_AD1_B); job.dalpha = GB(i, FERVIT_B_ALPHA);
+        job.s2 = spb; job.s1 = spb; job.chunks = AD_CPB; job.E = E; job.A = A;
+        ad_jobs.push_back(job);
+      }
+    }
   }
   if (!ad_jobs.empty()) FV_TRY(adapter_grad_finalize(ad_jobs.data(), (int)ad_jobs.size(), b.ad_fin, st));
   return 0;

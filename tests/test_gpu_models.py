@@ -6,6 +6,8 @@ plus size-independent properties at BASELINE.json's full batch sizes.
 Gates (BASELINE.json north_star): logits and every gradient within 1e-4 (fp32 mode) / 2e-2 (bf16 mode) norm-wise
 relative error, identical top-1 predictions.
 """
+import os
+
 import pytest
 import torch
 
@@ -201,6 +203,43 @@ def test_hybrid_vit_base_adapter_vs_oracle(precision):
     _compare("hybrid_vitb_adapter_vs_oracle", precision, got, ref, {"B": B})
 
 
+@pytest.mark.gpu
+def test_hybrid_grouped_adapter_gradients_vs_oracle():
+    """T = 64 x 19 rows is a multiple of the GEMM k-block, so the bf16 plan keeps every block's dy / du and finishes
+    the AdapterModule gradients of all 12 blocks with one split-K launch per weight and one column-sum launch per bias
+    (plan.cu: ad_deferred); smaller batches (the test above) take the per-block form. Same oracle, same gates; the
+    launch count tells the two forms apart."""
+    import fer_vit_b200 as fv
+    from fer_vit_b200 import _lib
+    from oracle import baseline_models as BM
+    from oracle import reference_math as R
+    fv.set_default_precision("bf16")
+    sd = BM.hybrid_state_dict(seed=3)
+    for i in range(12):
+        sd[f"adapters.{i}.alpha"] = torch.ones(1) * (0.1 + 0.02 * i)
+    model = fv.create_hybrid_latent_vit(model_size="base", use_pretrained=False, freeze_transformer=True,
+                                        use_adapter=True, adapter_dim=64)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(12)
+    B = 64
+    x = 0.5 * torch.randn(B, 18, 512, generator=g) + 0.3 * torch.randn(1, 18, 512, generator=g)
+    y = torch.randint(0, 7, (B,), generator=g)
+    BM.hybrid_trainable(sd)
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, 12, True, m), sd, x, y)
+    n0 = _lib.launch_count()
+    got = step(model, x.cuda(), y.cuda())
+    grouped = _lib.launch_count() - n0
+    n0 = _lib.launch_count()
+    step(model, x[:63].cuda(), y[:63].cuda())     # T = 63 x 19 rows: not a multiple of 64, per-block form
+    per_block = _lib.launch_count() - n0
+    if os.environ.get("FERVIT_ADAPTER_DEFER", "1") != "0":
+        assert grouped < per_block, (grouped, per_block)   # 12 x 4 side launches became 4
+    _compare("hybrid_vitb_grouped_adapter_grads_vs_oracle", "bf16", got, ref, {"B": B, "launches": grouped,
+                                                                              "launches_per_block_form": per_block})
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_hybrid_head_dropout_train_mode(precision):
     """train(): the head's Dropout(0.1) is active; the oracle receives the very mask the kernel drew."""
