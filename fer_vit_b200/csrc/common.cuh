@@ -306,10 +306,27 @@ __host__ __device__ __forceinline__ uint64_t mix_hash64(uint64_t seed, uint32_t 
 __host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t site, uint64_t idx) {
   return (uint32_t)(mix_hash64(seed, site, idx) >> 32);
 }
+// The dropout generator proper. mix_hash64 costs ~25 integer instructions per element (three 64-bit multiplies), which
+// made the mask the largest instruction consumer of the attention kernels with dropout on (85 % of the S = 197 forward
+// kernel's instructions, profiles/r02_ncu_attn_long.txt). drop_hash keeps the 64-bit mix for the KEY only - one value
+// per (seed, site), loop-invariant in every kernel - and spends two 32-bit multiply-xorshift rounds per element
+// (lowbias32 constants), the second key word entering between the rounds so that different keys give different
+// functions, not translations of one. ~10 instructions per element.
+__host__ __device__ __forceinline__ uint32_t drop_hash(uint64_t seed, uint32_t site, uint64_t idx) {
+  const uint64_t key = mix_hash64(seed, site, 0x5DEECE66Dull);
+  uint32_t x = (uint32_t)idx * 0x9E3779B1u + (uint32_t)key;
+  x ^= x >> 16;
+  x *= 0x7FEB352Du;
+  x ^= (uint32_t)(key >> 32) + (uint32_t)(idx >> 32) * 0x85EBCA6Bu;
+  x ^= x >> 15;
+  x *= 0x846CA68Bu;
+  x ^= x >> 16;
+  return x;
+}
 // threshold = round(p * 2^32); keep iff hash >= threshold
 __host__ __device__ __forceinline__ bool drop_keep(uint64_t seed, uint32_t site, uint64_t idx,
                                                    uint32_t threshold) {
-  return mix_hash(seed, site, idx) >= threshold;
+  return drop_hash(seed, site, idx) >= threshold;
 }
 static inline uint32_t drop_threshold(float p) {
   double t = (double)p * 4294967296.0;

@@ -310,18 +310,37 @@ def mix_hash64(seed: int, site: int, idx):
 
 
 def mix_hash(seed: int, site: int, idx):
-    """Its high word: the dropout generator of the kernels (common.cuh: mix_hash)."""
+    """Its high word (common.cuh: mix_hash): the generator of the data path's draws."""
     import numpy as np
     return (mix_hash64(seed, site, idx) >> np.uint64(32)).astype(np.uint32)
 
 
+def drop_hash(seed: int, site: int, idx):
+    """The kernels' dropout generator (common.cuh: drop_hash): a 64-bit key per (seed, site) from mix_hash64, then two
+    32-bit multiply-xorshift rounds per element, the key's high word (and the index's) entering between them."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        idx = np.asarray(idx, dtype=np.uint64)
+        key = int(mix_hash64(seed, site, [0x5DEECE66D])[0])
+        k1, k2 = np.uint32(key & 0xFFFFFFFF), np.uint32(key >> 32)
+        lo = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        hi = (idx >> np.uint64(32)).astype(np.uint32)
+        x = lo * np.uint32(0x9E3779B1) + k1
+        x = x ^ (x >> np.uint32(16))
+        x = x * np.uint32(0x7FEB352D)
+        x = x ^ (k2 + hi * np.uint32(0x85EBCA6B))
+        x = x ^ (x >> np.uint32(15))
+        x = x * np.uint32(0x846CA68B)
+        return x ^ (x >> np.uint32(16))
+
+
 def dropout_keep(seed: int, site: int, idx, p: float):
     """keep-mask of the kernels' counter-based dropout (common.cuh: drop_keep / drop_threshold): element `idx` of
-    dropout site `site` survives iff the 32-bit mix is >= floor(p * 2^32); survivors are scaled by 1 / (1 - p)."""
+    dropout site `site` survives iff drop_hash is >= floor(p * 2^32); survivors are scaled by 1 / (1 - p)."""
     import numpy as np
     t = float(np.float32(p)) * 4294967296.0
     thr = 0 if t <= 0 else (4294967295 if t >= 4294967295.0 else int(t))
-    return torch.from_numpy(mix_hash(seed, site, idx) >= np.uint32(thr))
+    return torch.from_numpy(drop_hash(seed, site, idx) >= np.uint32(thr))
 
 
 def latent_augment_draws(seed: int, B: int, row: int, scale_range=None, mask_prob: float = 0.0):

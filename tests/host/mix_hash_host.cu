@@ -13,6 +13,12 @@ int main(int argc, char** argv) {
     const unsigned long long idx = strtoull(argv[i + 2], nullptr, 0);
     printf("%llu %u\n", (unsigned long long)fervit::mix_hash64(seed, site, idx), fervit::mix_hash(seed, site, idx));
   }
+  {  // the dropout generator at and beyond 32-bit indices
+    const unsigned long long idxs[4] = {0ull, 77ull, 0xFFFFFFFFull, (1ull << 40) + 7ull};
+    printf("H");
+    for (int k = 0; k < 4; ++k) printf(" %u", fervit::drop_hash(0xC0FFEEull, 0x4C41u + k, idxs[k]));
+    printf("\n");
+  }
   {  // keep-mask of 64 consecutive elements of one dropout site at p = 0.1 and p = 0.5, as bit strings
     const float ps[2] = {0.1f, 0.5f};
     for (int k = 0; k < 2; ++k) {

@@ -172,6 +172,32 @@ def test_decomposer_host_surface():
         d.decompose(torch.randn(2, 18, 64), mode="nope")
 
 
+def test_dropout_generator_statistics():
+    """drop_hash (two 32-bit rounds under a 64-bit key): keep rate, independence of neighbouring elements, of
+    consecutive seeds (a graph replay = seed + 1) and of sites, on 2^20 elements; bit balance of the raw hash."""
+    n = 1 << 20
+    idx = np.arange(n)
+    for p in (0.1, 0.5):
+        a = R.dropout_keep(1234, 8, idx, p).numpy()
+        b = R.dropout_keep(1235, 8, idx, p).numpy()
+        c = R.dropout_keep(1234, 9, idx, p).numpy()
+        tol = 5 * np.sqrt(p * (1 - p) / n)
+        for m in (a, b, c):
+            assert abs(m.mean() - (1 - p)) < tol
+        for u, v in ((a[:-1], a[1:]), (a[:-197], a[197:]), (a, b), (a, c), (a[:-1], b[1:]), (a[1:], b[:-1])):
+            corr = np.corrcoef(u.astype(np.float64), v.astype(np.float64))[0, 1]
+            assert abs(corr) < 5 / np.sqrt(n), corr
+    h = R.drop_hash(99, 3, idx)
+    for bit in range(32):
+        frac = float(((h >> np.uint32(bit)) & np.uint32(1)).mean())
+        assert abs(frac - 0.5) < 5 * 0.5 / np.sqrt(n), (bit, frac)
+    # rows of an attention matrix (index = row * S + col) must not repeat each other's masks
+    rows = R.dropout_keep(7, 0, idx[:197 * 197], 0.1).numpy().reshape(197, 197).astype(np.float64)
+    cc = np.corrcoef(rows)
+    off = cc[~np.eye(197, dtype=bool)]
+    assert np.abs(off).max() < 6 / np.sqrt(197) and abs(off.mean()) < 0.01
+
+
 def test_generator_restatement_matches_the_c_source(tmp_path):
     """The kernels' counter-based generator (csrc/common.cuh, __host__ __device__) compiled for the HOST and run here:
     the oracle's numpy mix_hash64 / mix_hash give the same 64- and 32-bit values, and the dropout threshold rounding is
@@ -195,6 +221,11 @@ def test_generator_restatement_matches_the_c_source(tmp_path):
         assert int(R.mix_hash64(seed, site, [idx])[0]) == h64, (seed, site, idx)
         assert int(R.mix_hash(seed, site, [idx])[0]) == h32
         assert h32 == h64 >> 32
+    hline = lines[len(cases)].split()
+    assert hline[0] == "H"
+    for k, idx in enumerate((0, 77, 0xFFFFFFFF, 2 ** 40 + 7)):
+        assert int(R.drop_hash(0xC0FFEE, 0x4C41 + k, [idx])[0]) == int(hline[1 + k]), idx
+    lines = lines[:len(cases)] + lines[len(cases) + 1:]
     for line, p in zip(lines[len(cases):len(cases) + 2], (0.1, 0.5)):
         keep = R.dropout_keep(12345, 9, np.arange(1000, 1064), p)
         assert line.split()[1] == "".join("1" if k else "0" for k in keep.tolist()), p
