@@ -248,10 +248,7 @@ FV_API int fervit_layernorm_backward(int act_dtype, const void* dy, const float*
   }
   if (wg) {
     const int g = layernorm_bwd_grid(rows);
-    float* tmp = scratch + (size_t)g * 2 * E;
-    FV_TRY(colsum_reduce_partials(scratch, g, 2 * E, tmp, S_(stream)));
-    FV_CUDA(cudaMemcpyAsync(dgamma, tmp, E * sizeof(float), cudaMemcpyDeviceToDevice, S_(stream)));
-    FV_CUDA(cudaMemcpyAsync(dbeta, tmp + E, E * sizeof(float), cudaMemcpyDeviceToDevice, S_(stream)));
+    FV_TRY(colsum_reduce_partials(scratch, g, 2 * E, dgamma, S_(stream), dbeta, E));
   }
   return 0;
 }

@@ -267,7 +267,7 @@ colsum_partial_kernel(const T* __restrict__ in, int R, int C, long long ld, int 
 // even 256 partial rows are 8 independent loads per thread; the row lanes are combined in a fixed order
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const float* alpha_ptr, float alpha,
-                    float* __restrict__ out) {
+                    float* __restrict__ out, float* __restrict__ out_hi, int split) {
   __shared__ float4 red[32][8];
   pdl_trigger();
   pdl_grid_sync();
@@ -290,7 +290,9 @@ colsum_final_kernel(const float* __restrict__ partial, int chunks, int C, const 
       t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
     }
     if (alpha_ptr) alpha *= __ldg(alpha_ptr);
-    *reinterpret_cast<float4*>(out + c) = make_float4(t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha);
+    // columns [split, C) may go to a second tensor (LayerNorm: [gamma | beta] partial rows -> two gradients)
+    float* dst = (out_hi && c >= split) ? out_hi + (c - split) : out + c;
+    *reinterpret_cast<float4*>(dst) = make_float4(t.x * alpha, t.y * alpha, t.z * alpha, t.w * alpha);
   }
 }
 
@@ -536,7 +538,7 @@ int colsum(const T* in, int R, int C, long long ld, float* scratch, const float*
   FV_CUDA(launch_pdl(ew::colsum_partial_kernel<T>, grid, block, 0, stream, in, R, C, ld, rpc, scratch, drop));
   FV_COUNT_LAUNCH();
   FV_CUDA(launch_pdl(ew::colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(8, 32), 0, stream, (const float*)scratch, chunks,
-                     C, alpha_ptr, alpha, out));
+                     C, alpha_ptr, alpha, out, (float*)nullptr, 0));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;
@@ -546,10 +548,12 @@ template int colsum<float>(const float*, int, int, long long, float*, const floa
 template int colsum<bf16>(const bf16*, int, int, long long, float*, const float*, float, float*, Dropout,
                           cudaStream_t);
 
-int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream) {
-  FV_CHECK(C % 4 == 0, "colsum_reduce_partials: column count must be a multiple of 4");
+// columns [0, split) -> out, [split, C) -> out_hi (when given)
+int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream, float* out_hi,
+                           int split) {
+  FV_CHECK(C % 4 == 0 && split % 4 == 0, "colsum_reduce_partials: column counts must be multiples of 4");
   FV_CUDA(launch_pdl(ew::colsum_final_kernel, dim3(ceil_div(C, 32)), dim3(8, 32), 0, stream, partial, chunks, C,
-                     (const float*)nullptr, 1.0f, out));
+                     (const float*)nullptr, 1.0f, out, out_hi, split));
   FV_COUNT_LAUNCH();
   FV_LAUNCH_CHECK();
   return 0;

@@ -63,7 +63,8 @@ int colsum_chunks(int R);
 template <typename T>
 int colsum(const T* in, int R, int C, long long ld, float* scratch, const float* alpha_ptr, float alpha, float* out,
            Dropout drop, cudaStream_t stream);
-int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream);
+int colsum_reduce_partials(const float* partial, int chunks, int C, float* out, cudaStream_t stream,
+                           float* out_hi = nullptr, int split = 0);
 int splitk_reduce(const float* partial, int splits, size_t n, const float* alpha_ptr, float alpha, float* out,
                   cudaStream_t stream);
 template <typename T>

@@ -747,11 +747,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
           if (part) {
             const int g = layernorm_bwd_grid(T);
             // partial layout [g][2][E]: gamma rows then beta rows -> reduce as a [g, 2E] matrix into a temp pair
-            FV_TRY(colsum_reduce_partials(part, g, 2 * E, b.scratch + (size_t)g * 2 * E, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN2_W), b.scratch + (size_t)g * 2 * E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN2_B), b.scratch + (size_t)g * 2 * E + E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
+            FV_CHECK(GB(i, FERVIT_B_LN2_B), "backward: LayerNorm gradients must be requested together");
+            FV_TRY(colsum_reduce_partials(part, g, 2 * E, GB(i, FERVIT_B_LN2_W), st, GB(i, FERVIT_B_LN2_B), E));
           }
           cur ^= 1;
         }
@@ -783,11 +780,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
                                         DX(cur ^ 1), at_out, part, nodrop, st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
-            FV_TRY(colsum_reduce_partials(part, g, 2 * E, b.scratch + (size_t)g * 2 * E, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN1_W), b.scratch + (size_t)g * 2 * E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN1_B), b.scratch + (size_t)g * 2 * E + E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
+            FV_CHECK(GB(i, FERVIT_B_LN1_B), "backward: LayerNorm gradients must be requested together");
+            FV_TRY(colsum_reduce_partials(part, g, 2 * E, GB(i, FERVIT_B_LN1_W), st, GB(i, FERVIT_B_LN1_B), E));
           }
           cur ^= 1;
         }
@@ -800,11 +794,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
                                            DX(cur ^ 1), (AT*)b.d_e1, part, cx.site(i, 3), st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
-            FV_TRY(colsum_reduce_partials(part, g, 2 * E, b.scratch + (size_t)g * 2 * E, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN2_W), b.scratch + (size_t)g * 2 * E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN2_B), b.scratch + (size_t)g * 2 * E + E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
+            FV_CHECK(GB(i, FERVIT_B_LN2_B), "backward: LayerNorm gradients must be requested together");
+            FV_TRY(colsum_reduce_partials(part, g, 2 * E, GB(i, FERVIT_B_LN2_W), st, GB(i, FERVIT_B_LN2_B), E));
           }
           cur ^= 1;
         }
@@ -831,11 +822,8 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
                                            DX(cur ^ 1), (AT*)b.d_e1, part, cx.site(i, 1), st)));
           if (part) {
             const int g = layernorm_bwd_grid(T);
-            FV_TRY(colsum_reduce_partials(part, g, 2 * E, b.scratch + (size_t)g * 2 * E, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN1_W), b.scratch + (size_t)g * 2 * E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
-            FV_CUDA(cudaMemcpyAsync(GB(i, FERVIT_B_LN1_B), b.scratch + (size_t)g * 2 * E + E, E * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, st));
+            FV_CHECK(GB(i, FERVIT_B_LN1_B), "backward: LayerNorm gradients must be requested together");
+            FV_TRY(colsum_reduce_partials(part, g, 2 * E, GB(i, FERVIT_B_LN1_W), st, GB(i, FERVIT_B_LN1_B), E));
           }
           cur ^= 1;
         }
