@@ -637,10 +637,11 @@ def run_dp_check(torch, dist, fv, model, opt, dev, shape, rank, world):
     identical = all(bool(torch.equal(all_bits[0], b)) for b in all_bits[1:])
     if was_training:
         model.train()
-    tol = 1e-4
+    tol, tol_tensor = 1e-4, 1e-3   # whole gradient / any single tensor (small bias tensors carry the rounding noise)
     return {"dp_grad_vs_single_gpu_global_batch_relerr": float(err.item()),
-            "worst_tensor_relerr": float(worst.item()), "tolerance": tol,
-            "grad_ok": bool(err.item() < tol), "replicas_bit_identical_after_training_steps": identical,
+            "worst_tensor_relerr": float(worst.item()), "tolerance": tol, "worst_tensor_tolerance": tol_tensor,
+            "grad_ok": bool(err.item() < tol and worst.item() < tol_tensor),
+            "replicas_bit_identical_after_training_steps": identical,
             "global_batch": Bc * world, "tensors": len(named),
             "note": "whole-gradient and worst-tensor relative error (max over ranks) between the NCCL-averaged "
                     "gradient of a sharded batch and the gradient of the same global batch computed on one GPU, "

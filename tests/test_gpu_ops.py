@@ -286,6 +286,7 @@ def attn_ref(qkv, B, S, H, hd, mask=None):
                                             (2, 197, 8, 64, 0.0), (2, 197, 8, 48, 0.0), (4, 19, 8, 64, 0.1),
                                             (2, 5, 2, 32, 0.1), (2, 197, 4, 64, 0.1), (3, 100, 2, 32, 0.1),
                                             (2, 256, 2, 64, 0.0), (1, 33, 3, 48, 0.0), (2, 130, 2, 64, 0.1),
+                                            (2, 256, 2, 64, 0.1), (2, 209, 2, 48, 0.1),   # > 208 keys: 8 warps, two rounds
                                             # persistent short-sequence kernel: several problems per warp pair (the
                                             # double-buffered loop), a ragged last CTA, one 16-row tile only, S = 32
                                             (256, 19, 12, 64, 0.0), (131, 19, 3, 64, 0.1), (300, 12, 6, 32, 0.1),
