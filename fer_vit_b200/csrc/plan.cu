@@ -898,6 +898,7 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
       FV_TRY(colsum_partial_rows<AT>(AD_DY(ad_lo), n * T, E, E, rpc, b.ad_csdy_pool, st));
       FV_TRY(colsum_partial_rows<AT>(AD_DU(ad_lo), n * T, A, A, rpc, b.ad_csdu_pool, st));
       for (int i = ad_lo; i <= ad_hi; ++i) {
+        if (!GB(i, FERVIT_B_AD2_W)) continue;   // a frozen adapter inside the range: its slabs are simply not used
         const int g = i - ad_lo;
         AdapterGradJob job;
         job.w2_part = b.ad_w2_pool + (size_t)g * spb * E * A;

@@ -237,6 +237,15 @@ def test_hybrid_grouped_adapter_gradients_vs_oracle():
         assert grouped < per_block, (grouped, per_block)   # 12 x 4 side launches became 4
     _compare("hybrid_vitb_grouped_adapter_grads_vs_oracle", "bf16", got, ref, {"B": B, "launches": grouped,
                                                                               "launches_per_block_form": per_block})
+    # one adapter frozen in the middle of the grouped range: its gradients are absent, every other one is unchanged
+    for k, p in model.named_parameters():
+        if k.startswith("adapters.5."):
+            p.requires_grad_(False)
+    part = step(model, x.cuda(), y.cuda())[2]
+    assert not any(k.startswith("adapters.5.") for k in part)
+    assert set(part) == {k for k in got[2] if not k.startswith("adapters.5.")}
+    for k, v in part.items():
+        assert torch.equal(v, got[2][k]), k
 
 
 @pytest.mark.gpu
