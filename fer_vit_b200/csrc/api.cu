@@ -180,6 +180,8 @@ static int op_wgrad_splits(int act_dtype, int M, int N, int K) {
   // same policy as the plan (plan.cu: wgrad_splits), restated on the public shapes: dW[N,K] reduced over M rows
   const int sms = num_sms();
   if (act_dtype == FERVIT_BF16) {
+    const int s2 = gemm_wgrad2_splits(N, K, M);   // shapes the CTA-pair kernel takes: one 256 x 256 unit per pair
+    if (s2 > 0) return s2;
     const int tiles = ceil_div(N, 128) * ceil_div(K, 128);
     int s = sms / (tiles > 0 ? tiles : 1);
     const int max_s = ceil_div(M, 256);

@@ -493,6 +493,11 @@ int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool
   const int kind2 = epilogue_kind_nodrop(epi);   // the CTA-pair kernel takes dropout as a flag beside the kind
   if (!a_mn && !b_mn && p.splits == 1 && force_bn >= 0 && gemm_bf16_tc2_supported(M, N, K, lda, ldb, epi, kind2))
     return gemm_bf16_tc2(A, lda, B, ldb, M, N, K, force_bn, epi, kind2, stream);
+  // weight gradients (both operands MN-major, plain fp32 slabs) of 256-wide shapes: the CTA-pair kernel of gemm_wgrad2.cu
+  if (a_mn && b_mn && force_bn >= 0 && kind == EPK_PLAIN && epi.out_f32 != nullptr && epi.out == nullptr &&
+      epi.bias == nullptr && epi.residual == nullptr && epi.remap_L == 0 && epi.ldo == N && !epi.drop.threshold &&
+      gemm_wgrad2_supported(M, N, K, lda, ldb))
+    return gemm_wgrad2(A, lda, B, ldb, M, N, K, p.splits, p.kb_per_split, epi.out_f32, epi.alpha_ptr, epi.alpha, stream);
   FV_CHECK(!epi.ln_part && !epi.lnp_part, "gemm_bf16_tc: a folded LayerNorm needs the CTA-pair kernel, which does not "
            "support this problem (M=%d N=%d K=%d)", M, N, K);
   if (force_bn < 0) force_bn = -force_bn;  // negative: force this kernel with that tile width (benchmarks)

@@ -9,6 +9,11 @@ namespace fervit {
 int gemm_bf16_tc(const bf16* A, int lda, bool a_mn, const bf16* B, int ldb, bool b_mn, int M, int N, int K, int splits,
                  int force_bn, const Epilogue& epi, cudaStream_t stream);
 int gemm_bf16_tc_effective_splits(int K, int splits);
+// CTA-pair weight-gradient GEMM (gemm_wgrad2.cu): dW[M,N] = A^T B over K token rows, A [K,M], B [K,N], fp32 slabs
+bool gemm_wgrad2_supported(int M, int N, int K, int lda, int ldb);
+int gemm_wgrad2_splits(int M, int N, int K);
+int gemm_wgrad2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int splits, int kb_per_split,
+                float* out, const float* alpha_ptr, float alpha, cudaStream_t stream);
 // gemm_tc2.cu (CTA-pair kernel; K-major operands, TMA epilogue)
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind);
 int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn, const Epilogue& e,

@@ -186,6 +186,8 @@ long long slot_numel(const fervit_plan* p, int slot) {
 int wgrad_splits(bool bf16_mode, int Nout, int Kin, int T) {
   const int sms = num_sms();
   if (bf16_mode) {
+    const int s2 = gemm_wgrad2_splits(Nout, Kin, T);   // shapes the CTA-pair kernel takes (gemm_wgrad2.cu)
+    if (s2 > 0) return s2;
     const int tiles = ceil_div(Nout, 128) * ceil_div(Kin, 128);
     int s = sms / (tiles > 0 ? tiles : 1);
     const int max_s = ceil_div(T, 256);  // at least 4 k-blocks of 64 per split

@@ -214,7 +214,11 @@ def test_gemm_bf16_tcgen05_stream_k(lib, M, N, K):
 
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K", [(256, 64, 64), (4864, 64, 768), (4864, 768, 64), (608, 1536, 512),
-                                   (1000, 128, 208), (4608, 768, 512), (4864, 768, 3072)])
+                                   (1000, 128, 208), (4608, 768, 512), (4864, 768, 3072),
+                                   # CTA-pair kernel (gemm_wgrad2.cu): N, K >= 256; ragged token tail, ragged 256-tiles,
+                                   # one unit per pair and several, the configs' real shapes
+                                   (9728, 2048, 512), (12608, 512, 2048), (2100, 320, 256), (2048, 256, 448),
+                                   (9728, 1536, 512), (12608, 512, 768)])
 def test_linear_wgrad(lib, dtype_name, M, N, K):
     """dW[N,K] = alpha * dY^T X over M token rows: MN-major tcgen05 operands (bf16) / strided fp32 GEMM, split-K."""
     L = lib
