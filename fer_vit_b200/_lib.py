@@ -100,6 +100,8 @@ SIGNATURES = {
     "fervit_linear_dgrad": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "fervit_linear_wgrad_scratch_floats": (_ll, [_i, _i, _i]),
     "fervit_linear_wgrad": (_i, [_i, _p, _p, _i, _i, _i, _f, _p, _p, _p]),
+    "fervit_linear_wgrad_bias_scratch_floats": (_ll, [_i, _i, _i]),
+    "fervit_linear_wgrad_bias": (_i, [_i, _p, _p, _i, _i, _i, _f, _p, _p, _p, _p]),
     "fervit_layernorm_forward": (_i, [_i, _p, _p, _p, _f, _i, _i, _p, _p, _p, _p, _p]),
     "fervit_layernorm_scratch_floats": (_ll, [_i, _i]),
     "fervit_layernorm_backward": (_i, [_i, _p, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),

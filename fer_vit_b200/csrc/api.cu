@@ -220,6 +220,29 @@ FV_API int fervit_linear_wgrad(int act_dtype, const void* dY, const void* X, int
   return 0;
 }
 
+FV_API long long fervit_linear_wgrad_bias_scratch_floats(int M, int N, int K) {
+  return fervit_linear_wgrad_scratch_floats(M, N, K) + 256ll * N;
+}
+
+FV_API int fervit_linear_wgrad_bias(int act_dtype, const void* dY, const void* X, int M, int N, int K, float alpha,
+                                    float* dW, float* db, float* scratch, void* stream) {
+  FV_CHECK(dY && X && dW && db && scratch, "linear_wgrad_bias: null argument");
+  if (act_dtype == FERVIT_BF16 && gemm_wgrad2_supported(N, K, M, N, K)) {
+    // one launch: the CTA-pair kernel adds up the dY tiles it stages for the weight gradient
+    const int splits = op_wgrad_splits(act_dtype, M, N, K);
+    const int per = ceil_div(ceil_div(M, 64), splits);
+    float* cs = scratch + (size_t)splits * N * K;
+    FV_TRY(gemm_wgrad2((const bf16*)dY, N, (const bf16*)X, K, N, K, M, splits, per, splits > 1 ? scratch : dW, nullptr,
+                       splits > 1 ? 1.0f : alpha, S_(stream), cs));
+    if (splits > 1) FV_TRY(splitk_reduce(scratch, splits, (size_t)N * K, nullptr, alpha, dW, S_(stream)));
+    return colsum_reduce_partials(cs, 2 * splits, N, db, S_(stream));
+  }
+  FV_TRY(fervit_linear_wgrad(act_dtype, dY, X, M, N, K, alpha, dW, scratch, stream));
+  const Dropout nd = make_dropout(0.f, 0, 0);
+  if (act_dtype == FERVIT_F32) return colsum<float>((const float*)dY, M, N, N, scratch, nullptr, 1.0f, db, nd, S_(stream));
+  return colsum<bf16>((const bf16*)dY, M, N, N, scratch, nullptr, 1.0f, db, nd, S_(stream));
+}
+
 FV_API int fervit_layernorm_forward(int act_dtype, const float* x, const float* gamma, const float* beta, float eps,
                                     int rows, int E, float* y_f32, void* y_act, float* mean, float* rstd,
                                     void* stream) {

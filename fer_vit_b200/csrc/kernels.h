@@ -12,8 +12,9 @@ int gemm_bf16_tc_effective_splits(int K, int splits);
 // CTA-pair weight-gradient GEMM (gemm_wgrad2.cu): dW[M,N] = A^T B over K token rows, A [K,M], B [K,N], fp32 slabs
 bool gemm_wgrad2_supported(int M, int N, int K, int lda, int ldb);
 int gemm_wgrad2_splits(int M, int N, int K);
+// colsum (optional): [2 * splits][M] slabs of the column sums of A over each split's token rows (the bias gradient)
 int gemm_wgrad2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int splits, int kb_per_split,
-                float* out, const float* alpha_ptr, float alpha, cudaStream_t stream);
+                float* out, const float* alpha_ptr, float alpha, cudaStream_t stream, float* colsum = nullptr);
 // gemm_tc2.cu (CTA-pair kernel; K-major operands, TMA epilogue)
 bool gemm_bf16_tc2_supported(int M, int N, int K, int lda, int ldb, const Epilogue& e, int kind);
 int gemm_bf16_tc2(const bf16* A, int lda, const bf16* B, int ldb, int M, int N, int K, int force_bn, const Epilogue& e,

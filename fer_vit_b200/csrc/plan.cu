@@ -241,7 +241,7 @@ size_t scratch_floats_for(const fervit_plan* p, int B) {
   const int T = B * p->S, Tl = B * c.L;
   size_t m = 1024;
   auto upd = [&](size_t v) { if (v > m) m = v; };
-  auto wg = [&](int Nout, int Kin, int rows) { upd((size_t)wgrad_splits(bf, Nout, Kin, rows) * Nout * Kin); };
+  auto wg = [&](int Nout, int Kin, int rows) { upd((size_t)wgrad_splits(bf, Nout, Kin, rows) * ((size_t)Nout * Kin + 2 * Nout)); };
   wg(c.E, c.Din, Tl);
   wg(3 * c.E, c.E, T); wg(c.E, c.E, T); wg(c.F, c.E, T); wg(c.E, c.F, T);
   if (c.adapter_dim) { wg(c.adapter_dim, c.E, T); wg(c.E, c.adapter_dim, T); }
@@ -396,11 +396,27 @@ int linear(const Ctx& c, const AT* A, int M, int slot, bool transposed, const Ep
 }
 
 // dW[Nout,Kin] = alpha * dY^T X, reduced over T rows (tokens); deterministic split-K.
+// db (optional, bf16 mode): the bias gradient colsum(dY) from the same launch when the CTA-pair kernel takes the shape
+// (gemm_wgrad2.cu adds the dY tiles up while they sit in shared memory); *did_bias tells the caller whether it did.
 template <typename AT>
 int wgrad(const Ctx& c, const AT* dY, int Nout, const AT* X, int Kin, int T, const float* alpha_ptr, float* dW,
-          float* scratch) {
+          float* scratch, float* db = nullptr, bool* did_bias = nullptr) {
   const bool bf = !std::is_same<AT, float>::value;
   const int splits = wgrad_splits(bf, Nout, Kin, T);
+  if (did_bias) *did_bias = false;
+  if constexpr (!std::is_same<AT, float>::value) {
+    if (db && did_bias && gemm_wgrad2_supported(Nout, Kin, T, Nout, Kin)) {
+      const int total_kb = ceil_div(T, 64), per = ceil_div(total_kb, splits);
+      float* slabs = scratch;
+      float* cs = scratch + (size_t)splits * Nout * Kin;
+      FV_TRY(gemm_wgrad2(dY, Nout, X, Kin, Nout, Kin, T, splits, per, splits > 1 ? slabs : dW,
+                         splits > 1 ? nullptr : alpha_ptr, 1.0f, c.st, cs));
+      if (splits > 1) FV_TRY(splitk_reduce(slabs, splits, (size_t)Nout * Kin, alpha_ptr, 1.0f, dW, c.st));
+      FV_TRY(colsum_reduce_partials(cs, 2 * splits, Nout, db, c.st));
+      *did_bias = true;
+      return 0;
+    }
+  }
   Epilogue e = make_epilogue();
   e.ldo = Kin;
   if (splits > 1) {
@@ -803,15 +819,21 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
         const AT* dy2 = (const AT*)b.d_e1;  // masked dr2
         if (GB(i, FERVIT_B_FC2_W)) {
-          FV_TRY(wgrad<AT>(cx, dy2, E, (const AT*)k.g1, F, T, nullptr, GB(i, FERVIT_B_FC2_W), b.scratch));
-          FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
+          bool did = false;   // dy2 IS the masked gradient, so its column sums are the bias gradient
+          FV_TRY(wgrad<AT>(cx, dy2, E, (const AT*)k.g1, F, T, nullptr, GB(i, FERVIT_B_FC2_W), b.scratch,
+                           GB(i, FERVIT_B_FC2_B), &did));
+          if (!did)
+            FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
         }
         Epilogue e = make_epilogue();
         e.act_bwd = ACT_DERIV; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
         FV_TRY(linear<AT>(cx, dy2, T, p->bslot(i, FERVIT_B_FC2_W), true, e));
         if (GB(i, FERVIT_B_FC1_W)) {
-          FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch));
-          FV_TRY(colsum<AT>((const AT*)b.d_big, T, F, F, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC1_B), nodrop, st));
+          bool did = false;
+          FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch,
+                           GB(i, FERVIT_B_FC1_B), &did));
+          if (!did)
+            FV_TRY(colsum<AT>((const AT*)b.d_big, T, F, F, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC1_B), nodrop, st));
         }
         e = make_epilogue();
         e.residual = DX(cur); e.out_f32 = DX(cur ^ 1); e.ldo = E;
@@ -831,8 +853,11 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
         const AT* dy1 = (const AT*)b.d_e1;  // masked dr1
         if (GB(i, FERVIT_B_PROJ_W)) {
-          FV_TRY(wgrad<AT>(cx, dy1, E, (const AT*)k.ao, E, T, nullptr, GB(i, FERVIT_B_PROJ_W), b.scratch));
-          FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_PROJ_B), cx.site(i, 1), st));
+          bool did = false;   // dy1 IS the masked gradient
+          FV_TRY(wgrad<AT>(cx, dy1, E, (const AT*)k.ao, E, T, nullptr, GB(i, FERVIT_B_PROJ_W), b.scratch,
+                           GB(i, FERVIT_B_PROJ_B), &did));
+          if (!did)
+            FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_PROJ_B), cx.site(i, 1), st));
         }
         e = make_epilogue();
         e.out = b.d_e2; e.ldo = E;
@@ -840,10 +865,12 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         FV_TRY(attention_bwd<AT>((const AT*)k.qkv, (const AT*)k.ao, (const AT*)b.d_e2, k.lse, (AT*)b.d_big, B, S, c.H,
                                  p->HD, cx.site(i, 0), st));
         if (GB(i, FERVIT_B_QKV_W)) {
+          bool did = false;
           FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, 3 * E, (const AT*)b.x_at[i], E, T, nullptr, GB(i, FERVIT_B_QKV_W),
-                           b.scratch));
-          FV_TRY(colsum<AT>((const AT*)b.d_big, T, 3 * E, 3 * E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_QKV_B), nodrop,
-                            st));
+                           b.scratch, GB(i, FERVIT_B_QKV_B), &did));
+          if (!did)
+            FV_TRY(colsum<AT>((const AT*)b.d_big, T, 3 * E, 3 * E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_QKV_B), nodrop,
+                              st));
         }
         e = make_epilogue();
         e.residual = DX(cur); e.out_f32 = DX(cur ^ 1); e.ldo = E;

@@ -290,6 +290,13 @@ int fervit_linear_dgrad(int act_dtype, const void* dy, const void* Wt, const voi
 long long fervit_linear_wgrad_scratch_floats(int M, int N, int K);
 int fervit_linear_wgrad(int act_dtype, const void* dY, const void* X, int M, int N, int K, float alpha, float* dW,
                         float* scratch, void* stream);
+/* The same plus the bias gradient db[N] = colsum(dY) (nn.Linear's bias.grad). bf16 shapes with N, K >= 256 and
+ * M >= 2048 rows take ONE launch of the CTA-pair kernel (csrc/gemm_wgrad2.cu), which adds up the dY tiles it stages for
+ * the weight gradient; everything else is fervit_linear_wgrad followed by a column-sum pass.
+ * scratch: fervit_linear_wgrad_bias_scratch_floats(M,N,K) floats. */
+long long fervit_linear_wgrad_bias_scratch_floats(int M, int N, int K);
+int fervit_linear_wgrad_bias(int act_dtype, const void* dY, const void* X, int M, int N, int K, float alpha, float* dW,
+                             float* db, float* scratch, void* stream);
 
 /* nn.LayerNorm over rows of fp32 x[rows,E]; y in act_dtype and/or fp32; mean/rstd [rows] saved for backward. */
 int fervit_layernorm_forward(int act_dtype, const float* x, const float* gamma, const float* beta, float eps, int rows,

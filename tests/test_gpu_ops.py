@@ -238,6 +238,35 @@ def test_linear_wgrad(lib, dtype_name, M, N, K):
     assert e < 2e-5
 
 
+@pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(9728, 2048, 512), (12608, 512, 2048), (2100, 320, 256), (4864, 768, 512),
+                                   (608, 1536, 512), (4864, 64, 768)])
+def test_linear_wgrad_with_bias_gradient(lib, dtype_name, M, N, K):
+    """dW and db = colsum(dY) from one call: the CTA-pair kernel's in-kernel column sums (bf16, N, K >= 256, M >= 2048)
+    and the two-pass fallback give the same answers as fp64 math; the fused form is deterministic (two calls agree bit
+    for bit)."""
+    L = lib
+    dtype = L.F32 if dtype_name == "fp32" else L.BF16
+    tdt = torch.float32 if dtype == L.F32 else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + 7 * N + K)
+    dY = (torch.randn(M, N, device="cuda", generator=g) + 0.1).to(tdt)
+    X = torch.randn(M, K, device="cuda", generator=g).to(tdt)
+    scratch = torch.empty(int(L.lib().fervit_linear_wgrad_bias_scratch_floats(M, N, K)), device="cuda")
+    outs = []
+    for _ in range(2):
+        dW = torch.full((N, K), float("nan"), device="cuda")
+        db = torch.full((N,), float("nan"), device="cuda")
+        L.check(L.lib().fervit_linear_wgrad_bias(dtype, dY.data_ptr(), X.data_ptr(), M, N, K, 0.5, dW.data_ptr(),
+                                                 db.data_ptr(), scratch.data_ptr(), st()))
+        torch.cuda.synchronize()
+        outs.append((dW, db))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    e_w = relerr(outs[0][0], 0.5 * (dY.double().t() @ X.double()))
+    e_b = relerr(outs[0][1], dY.double().sum(0))
+    record("linear_wgrad_bias", dtype=dtype_name, M=M, N=N, K=K, err_w=e_w, err_b=e_b)
+    assert e_w < 2e-5 and e_b < 2e-5
+
+
 # ------------------------------------------------------------------------------------------------ LayerNorm
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
 @pytest.mark.parametrize("rows,E", [(37, 64), (608, 512), (4864, 768), (130, 192)])
