@@ -739,15 +739,22 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
         // ---- MLP ----
         if (GB(i, FERVIT_B_FC2_W)) {
-          FV_TRY(wgrad<AT>(cx, DXA(cur), E, (const AT*)k.g1, F, T, nullptr, GB(i, FERVIT_B_FC2_W), b.scratch));
-          FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
+          // (the bias gradient comes out of the weight-gradient launch when the bf16 copy IS the gradient: no dropout)
+          bool did = false;
+          FV_TRY(wgrad<AT>(cx, DXA(cur), E, (const AT*)k.g1, F, T, nullptr, GB(i, FERVIT_B_FC2_W), b.scratch,
+                           cx.site(i, 3).threshold ? nullptr : GB(i, FERVIT_B_FC2_B), &did));
+          if (!did)
+            FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC2_B), cx.site(i, 3), st));
         }
         Epilogue e = make_epilogue();
         e.act_bwd = ACT_DERIV; e.aux = k.u1; e.out = b.d_big; e.ldo = F; e.drop = cx.site(i, 2);
         FV_TRY(linear<AT>(cx, DXA(cur), T, p->bslot(i, FERVIT_B_FC2_W), true, e));
         if (GB(i, FERVIT_B_FC1_W)) {
-          FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch));
-          FV_TRY(colsum<AT>((const AT*)b.d_big, T, F, F, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC1_B), nodrop, st));
+          bool did = false;
+          FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, F, (const AT*)k.xn2, E, T, nullptr, GB(i, FERVIT_B_FC1_W), b.scratch,
+                           GB(i, FERVIT_B_FC1_B), &did));
+          if (!did)
+            FV_TRY(colsum<AT>((const AT*)b.d_big, T, F, F, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_FC1_B), nodrop, st));
         }
         e = make_epilogue();
         e.out = b.d_e1; e.ldo = E;
@@ -772,8 +779,11 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         }
         // ---- attention ----
         if (GB(i, FERVIT_B_PROJ_W)) {
-          FV_TRY(wgrad<AT>(cx, DXA(cur), E, (const AT*)k.ao, E, T, nullptr, GB(i, FERVIT_B_PROJ_W), b.scratch));
-          FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_PROJ_B), nodrop, st));
+          bool did = false;
+          FV_TRY(wgrad<AT>(cx, DXA(cur), E, (const AT*)k.ao, E, T, nullptr, GB(i, FERVIT_B_PROJ_W), b.scratch,
+                           GB(i, FERVIT_B_PROJ_B), &did));
+          if (!did)
+            FV_TRY(colsum<float>(DX(cur), T, E, E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_PROJ_B), nodrop, st));
         }
         e = make_epilogue();
         e.out = b.d_e2; e.ldo = E;
@@ -781,10 +791,12 @@ int backward_impl(fervit_plan* p, const float* x, int B, void* ws, long long ws_
         FV_TRY(attention_bwd<AT>((const AT*)k.qkv, (const AT*)k.ao, (const AT*)b.d_e2, k.lse, (AT*)b.d_big, B, S, c.H,
                                  p->HD, cx.site(i, 0), st));
         if (GB(i, FERVIT_B_QKV_W)) {
+          bool did = false;
           FV_TRY(wgrad<AT>(cx, (const AT*)b.d_big, 3 * E, (const AT*)k.xn1, E, T, nullptr, GB(i, FERVIT_B_QKV_W),
-                           b.scratch));
-          FV_TRY(colsum<AT>((const AT*)b.d_big, T, 3 * E, 3 * E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_QKV_B), nodrop,
-                            st));
+                           b.scratch, GB(i, FERVIT_B_QKV_B), &did));
+          if (!did)
+            FV_TRY(colsum<AT>((const AT*)b.d_big, T, 3 * E, 3 * E, b.scratch, nullptr, 1.0f, GB(i, FERVIT_B_QKV_B), nodrop,
+                              st));
         }
         e = make_epilogue();
         e.out = b.d_e1; e.ldo = E;

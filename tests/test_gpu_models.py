@@ -249,6 +249,33 @@ def test_hybrid_grouped_adapter_gradients_vs_oracle():
 
 
 @pytest.mark.gpu
+def test_hybrid_full_finetune_2128_rows_vs_oracle():
+    """`freeze_transformer=False` (train_hybrid_latent_vit.py: --no_freeze) at 112 samples = 2128 token rows, bf16: every
+    block's weight AND bias gradients come from the CTA-pair kernel (gemm_wgrad2.cu: M, N >= 256, >= 2048 rows), norms
+    un-folded, adapters on the per-block path (2128 is not a multiple of 64). Same oracle, same gates."""
+    import fer_vit_b200 as fv
+    from oracle import baseline_models as BM
+    from oracle import reference_math as R
+    fv.set_default_precision("bf16")
+    sd = BM.hybrid_state_dict(seed=4)
+    for i in range(12):
+        sd[f"adapters.{i}.alpha"] = torch.ones(1) * (0.1 + 0.02 * i)
+    model = fv.create_hybrid_latent_vit(model_size="base", use_pretrained=False, freeze_transformer=False,
+                                        use_adapter=True, adapter_dim=64)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().eval()
+    g = torch.Generator().manual_seed(13)
+    B = 112
+    x = 0.5 * torch.randn(B, 18, 512, generator=g) + 0.3 * torch.randn(1, 18, 512, generator=g)
+    y = torch.randint(0, 7, (B,), generator=g)
+    BM.hybrid_trainable(sd, freeze_transformer=False)
+    ref = _oracle_step(lambda s, xx, m: R.hybrid_forward(s, xx, 12, 12, True, m), sd, x, y)
+    got = step(model, x.cuda(), y.cuda())
+    assert any(k.startswith("transformer.") for k in got[2])
+    _compare("hybrid_vitb_full_finetune_vs_oracle", "bf16", got, ref, {"B": B})
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_hybrid_head_dropout_train_mode(precision):
     """train(): the head's Dropout(0.1) is active; the oracle receives the very mask the kernel drew."""
@@ -272,9 +299,11 @@ def test_hybrid_head_dropout_train_mode(precision):
     _compare("hybrid_head_dropout", precision, got, ref)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_latent_vit_default_config_vs_oracle(precision):
-    """BASELINE config 1: LatentViT 512/d6/h8/2048 on 18x512 tokens, batch 32."""
+@pytest.mark.parametrize("precision,B", [("fp32", 32), ("bf16", 32), ("bf16", 112)])
+def test_latent_vit_default_config_vs_oracle(precision, B):
+    """BASELINE config 1: LatentViT 512/d6/h8/2048 on 18x512 tokens, batch 32. Batch 112 (2128 token rows) is past the
+    2048 rows from which the bf16 plan takes weight AND bias gradients from the CTA-pair kernel (gemm_wgrad2.cu), the
+    path configs 2 and 4 train on."""
     import fer_vit_b200 as fv
     from oracle import reference_math as R
     fv.set_default_precision(precision)
@@ -290,7 +319,7 @@ def test_latent_vit_default_config_vs_oracle(precision):
                     p.add_(0.02 * torch.randn_like(p))
     sd = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(42)
-    x = torch.randn(32, 18, 512, generator=g); y = torch.randint(0, 7, (32,), generator=g)
+    x = torch.randn(B, 18, 512, generator=g); y = torch.randint(0, 7, (B,), generator=g)
     model = model.cuda().train()
     model.plan_runner().keep_workspace = True
     import fer_vit_b200 as fv2
@@ -299,11 +328,12 @@ def test_latent_vit_default_config_vs_oracle(precision):
     loss = fv2.cross_entropy(logits, y.cuda(), None, 0.1)
     loss.backward()
     grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
-    sel = _relu_selectors(model, 6, 32, 19)
+    sel = _relu_selectors(model, 6, B, 19)
     ref = _relu_reference("latent_vit_cfg1", precision, lambda s, xx, m: R.latent_vit_forward(s, xx, 6, 8, m), sd, x, y,
                           sel, smoothing=0.1)
     base = _torch_autocast_step(model, x.cuda(), y.cuda(), 0.1) if precision == "bf16" else None
-    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref, baseline=base)
+    _compare("latent_vit_cfg1_vs_oracle", precision, (logits.detach(), loss.detach(), grads), ref, {"B": B},
+             baseline=base)
 
 
 @pytest.mark.parametrize("dims", [(64, 2, 128, 2, 5), (256, 4, 768, 2, 37)])
@@ -376,9 +406,10 @@ def test_latent_vit_v2_config4_vs_oracle(precision):
     _compare("latent_vit_v2_cfg4_vs_oracle", precision, got, ref, baseline=base)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_image_vit_config2_vs_oracle(precision):
-    """BASELINE config 2 shape: ImageViT 512/d6/h8/2048 on 224x224 (S = 197), reduced batch."""
+@pytest.mark.parametrize("precision,B", [("fp32", 3), ("bf16", 3), ("bf16", 11)])
+def test_image_vit_config2_vs_oracle(precision, B):
+    """BASELINE config 2 shape: ImageViT 512/d6/h8/2048 on 224x224 (S = 197), reduced batch. 11 images are 2167 token
+    rows: the CTA-pair weight + bias gradient kernel's path (gemm_wgrad2.cu) under the same oracle and gates."""
     import fer_vit_b200 as fv
     from oracle import reference_math as R
     fv.set_default_precision(precision)
@@ -390,11 +421,10 @@ def test_image_vit_config2_vs_oracle(precision):
                 p.add_(0.05 * torch.randn_like(p))
     sd = {k: v.detach().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     g = torch.Generator().manual_seed(44)
-    B = 3
     x = torch.randn(B, 3, 224, 224, generator=g); y = torch.randint(0, 7, (B,), generator=g)
     ref = _oracle_step(lambda s, xx, m: R.image_vit_forward(s, xx, 6, 8, 16, m), sd, x, y)
     got = step(model.cuda().train(), x.cuda(), y.cuda())
-    _compare("image_vit_cfg2_vs_oracle", precision, got, ref)
+    _compare("image_vit_cfg2_vs_oracle", precision, got, ref, {"B": B})
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
