@@ -596,7 +596,12 @@ def run_dp_check(torch, dist, fv, model, opt, dev, shape, rank, world):
     gradient of the concatenated global batch computed on one GPU; (2) after the optimizer steps of the timed regions
     (different data on every rank) all replicas still hold bit-identical parameters."""
     runner = model.plan_runner()
-    Bc = 64
+    # Per-rank batch of the check: both sides must take the same kernels, or the comparison measures two roundings
+    # instead of the reduction. The bf16 plan switches the weight / bias gradients to the CTA-pair kernel (bias gradient
+    # from the bf16 copy of dY) at 2048 token rows, so the 19-token models are checked at 128 samples per rank (2432 rows
+    # on a rank, more on the single-GPU side); the hybrid at 64 (grouped adapter gradients on both sides) and ImageViT at
+    # 64 (12608 rows) already are on one side of it.
+    Bc = 128 if (len(shape) == 2 and not hasattr(model, "adapters")) else 64
     g = torch.Generator(device=dev).manual_seed(777 + rank)
     x = torch.randn(Bc, *shape, device=dev, generator=g)
     y = torch.randint(0, 7, (Bc,), device=dev, generator=g)
@@ -646,8 +651,8 @@ def run_dp_check(torch, dist, fv, model, opt, dev, shape, rank, world):
             "note": "whole-gradient and worst-tensor relative error (max over ranks) between the NCCL-averaged "
                     "gradient of a sharded batch and the gradient of the same global batch computed on one GPU, "
                     "in the model's precision mode (the bf16 forward/dgrad are row-independent; only the fp32 "
-                    "reduction order of the weight gradients differs); parameter bit-checksums all-gathered after the "
-                    "timed AdamW steps"}
+                    "reduction order of the weight gradients differs), at a per-rank batch that keeps both sides on the "
+                    "same kernels; parameter bit-checksums all-gathered after the timed AdamW steps"}
 
 
 def run_config5(torch, dist, fv, model, opt, dev, rank, world, args, make_eager, live_graphs):
