@@ -307,3 +307,25 @@ def test_expression_aware_factory_matches_the_reference(tmp_path, output_mode):
     ref.load_state_dict(so, strict=True)            # a checkpoint of the drop-in loads into the reference, and back
     ours.load_state_dict(ref.state_dict(), strict=True)
     ours.print_info()
+
+
+def test_product_package_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's reference / cpu_baseline legs may
+    import it. The product package (Python and CUDA sources) must not mention it in an import, an include or a path."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|#\s*include\s+[\"<].*oracle)|sys\.path.*oracle|baseline/_ref")
+    bad = []
+    for base, _, files in os.walk(os.path.join(root, "fer_vit_b200")):
+        if "_build" in base or "__pycache__" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                for n, line in enumerate(open(os.path.join(base, f), errors="ignore"), 1):
+                    if pat.search(line):
+                        bad.append((os.path.join(base, f), n, line.strip()))
+    assert not bad, bad
+    # and the two allowed importers outside tests/ confine it to the legs named above
+    bench = open(os.path.join(root, "bench.py")).read()
+    for m in re.finditer(r"^(\s*)(from oracle|import oracle)", bench, re.M):
+        assert len(m.group(1)) >= 4, "bench.py imports oracle at module level"
